@@ -1,0 +1,700 @@
+// sq_api.cu -- the C ABI declared in include/seqarc_b200.h: context, device workspace, wave
+// planning and kernel orchestration.  Stands where one EncapFqzComp + SeqArcMemBuf pair stands in
+// the reference (ctor @0x42f2a0, doFqzEncode @0x42d2d0, doDecode @0x42eb60), for a batch of blocks.
+// There is no CPU path in this file: every coder runs in the kernels of sq_encode.cu / sq_decode.cu.
+#include "../../include/seqarc_b200.h"
+#include "sq_kernels.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Arena {
+    u8 *base = nullptr;
+    u64 cap = 0, used = 0;
+    void reset() { used = 0; }
+    void *take(u64 bytes) {
+        u64 a = (used + 255) & ~(u64)255;
+        if (a + bytes > cap) return nullptr;
+        used = a + bytes;
+        return base + a;
+    }
+};
+
+struct StageTimer {
+    std::vector<const char *> names;
+    std::vector<cudaEvent_t> ev;       // ev[i] .. ev[i+1] brackets names[i]
+    std::vector<std::pair<const char *, float>> acc;
+    size_t n = 0;
+    void begin(cudaStream_t st) { n = 0; names.clear(); mark(nullptr, st); }
+    void mark(const char *name, cudaStream_t st) {
+        if (n == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        cudaEventRecord(ev[n++], st);
+        if (name) names.push_back(name);
+    }
+    void collect() {       // after a stream sync
+        for (size_t i = 0; i < names.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            bool found = false;
+            for (auto &a : acc) if (a.first == names[i]) { a.second += ms; found = true; break; }
+            if (!found) acc.push_back({names[i], ms});
+        }
+    }
+    void destroy() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); }
+};
+
+}  // namespace
+
+struct sq_ctx {
+    sq_params p;
+    int nsm = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Arena arena;
+    std::string err;
+    // model snapshot
+    u8 *d_model = nullptr;
+    u64 model_len = 0;
+    // measurement
+    StageTimer timer;
+    u64 launches = 0;
+    int last_wave_blocks = 0;
+    // last encoded wave (debug fetch)
+    EncWave last{};
+    std::vector<BlockDesc> last_bd;
+    bool last_valid = false;
+    // pinned scratch for small D2H reads
+    u8 *h_pin = nullptr;
+    u64 h_pin_cap = 0;
+
+    u32 NS() const { return 7 + (u32)p.slevel; }
+    u32 nseq() const { return 1u << (2 * NS()); }
+    u32 nqual() const { return p.qlevel > 2 ? 0x100000u : 0x10000u; }
+    u64 snap_name_bytes() const { return p.id_rule ? 0 : 3ull * 256 * 776 + 8192ull * 392; }
+};
+
+#define CUDA_OK(c, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    (c)->err = std::string(#x) + ": " + cudaGetErrorString(e_); return SQ_ERR_CUDA; } } while (0)
+
+static u64 al16(u64 x) { return (x + 15) & ~(u64)15; }
+
+static int ensure_pin(sq_ctx *c, u64 bytes) {
+    if (bytes <= c->h_pin_cap) return SQ_OK;
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    c->h_pin = nullptr; c->h_pin_cap = 0;
+    CUDA_OK(c, cudaMallocHost((void **)&c->h_pin, bytes));
+    c->h_pin_cap = bytes;
+    return SQ_OK;
+}
+
+extern "C" const char *sq_version(void) { return "seqarc-b200 0.1 (SeqArc v1.6 stream format)"; }
+
+extern "C" const char *sq_last_error(const sq_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int sq_create(const sq_params *p, sq_ctx **out) {
+    if (!p || !out) { g_create_error = "null argument"; return SQ_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return SQ_ERR_NO_DEVICE;
+    }
+    if (p->device < 0 || p->device >= ndev) { g_create_error = "device ordinal out of range"; return SQ_ERR_ARG; }
+    if (p->slevel < 0 || p->slevel > 5) { g_create_error = "slevel must be 0..5 (order 7..12)"; return SQ_ERR_ARG; }
+    if (p->qlevel < 1 || p->qlevel > 3) { g_create_error = "qlevel must be 1..3"; return SQ_ERR_ARG; }
+    if (p->lossy && !(p->lossy_r > 1.0)) { g_create_error = "lossy_r must be > 1"; return SQ_ERR_ARG; }
+    sq_ctx *c = new sq_ctx();
+    c->p = *p;
+    auto fail = [&](const std::string &m, int code) { g_create_error = m; sq_destroy(c); return code; };
+    if ((e = cudaSetDevice(p->device)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, p->device)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
+    c->nsm = prop.multiProcessorCount;
+    if (p->stream) c->stream = (cudaStream_t)p->stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
+        c->own_stream = true;
+    }
+    u64 want = p->workspace_bytes;
+    if (want == 0) {
+        size_t fr = 0, tot = 0;
+        if ((e = cudaMemGetInfo(&fr, &tot)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
+        want = (u64)(fr * 0.8);
+    }
+    if ((e = cudaMalloc((void **)&c->arena.base, want)) != cudaSuccess)
+        return fail(std::string("workspace cudaMalloc: ") + cudaGetErrorString(e), SQ_ERR_NOMEM);
+    c->arena.cap = want;
+    if ((e = sqk_enc_attrs()) != cudaSuccess) return fail(std::string("kernel attributes: ") + cudaGetErrorString(e), SQ_ERR_CUDA);
+    *out = c;
+    return SQ_OK;
+}
+
+extern "C" void sq_destroy(sq_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->p.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->timer.destroy();
+    if (c->arena.base) cudaFree(c->arena.base);
+    if (c->d_model) cudaFree(c->d_model);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" uint64_t sq_model_size(const sq_ctx *c) {
+    if (!c) return 0;
+    return c->snap_name_bytes() + (u64)c->nseq() * 4 + (u64)c->nqual() * 293;
+}
+
+extern "C" int sq_load_model(sq_ctx *c, const uint8_t *blob, uint64_t len) {
+    if (!c || !blob) return SQ_ERR_ARG;
+    if (len != sq_model_size(c)) { c->err = "model snapshot has the wrong size for this slevel/qlevel/id_rule"; return SQ_ERR_ARG; }
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    if (c->d_model) { cudaFree(c->d_model); c->d_model = nullptr; }
+    CUDA_OK(c, cudaMalloc((void **)&c->d_model, len));
+    CUDA_OK(c, cudaMemcpy(c->d_model, blob, len, cudaMemcpyHostToDevice));
+    c->model_len = len;
+    return SQ_OK;
+}
+
+extern "C" int sq_last_timings(const sq_ctx *c, const char **names, float *ms, int cap) {
+    if (!c) return 0;
+    int n = 0;
+    for (auto &a : c->timer.acc) { if (n >= cap) break; names[n] = a.first; ms[n] = a.second; n++; }
+    return n;
+}
+extern "C" uint64_t sq_last_launches(const sq_ctx *c) { return c ? c->launches : 0; }
+extern "C" int sq_last_wave_blocks(const sq_ctx *c) { return c ? c->last_wave_blocks : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// encode
+namespace {
+
+struct BlkCost {
+    u64 inputs, perread, eb[ST_COUNT], obuf, side, rec;
+};
+
+const u32 NCTX_NAME = NK_TOTAL;
+
+BlkCost block_cost(const sq_ctx *c, const sq_block_in &b, bool host) {
+    BlkCost k{};
+    u64 n = b.nreads;
+    if (host) k.inputs = al16(b.idbytes) + 2 * al16(b.seqbytes) + al16(2 * n) + al16(4 * n) + 5 * 256;
+    if (c->p.lossy) k.inputs += al16(b.seqbytes) + 256;
+    k.perread = n * 27 + 9 * 256;
+    k.eb[ST_SEQ] = b.seqbytes;
+    k.eb[ST_QUAL] = b.seqbytes + n;
+    k.eb[ST_NAME] = c->p.id_rule ? 0 : b.idbytes + 3 * n;
+    k.obuf = 0;
+    for (int s = 0; s < ST_COUNT; s++) k.obuf += al16(2 * k.eb[s] + 16);
+    k.side = al16(16 * n + b.seqbytes / 2 + 4096);
+    k.rec = al16(256 + b.idbytes + 2 * b.seqbytes + 8 * n);
+    return k;
+}
+
+struct WaveAcc {
+    u64 lin = 0;                  // linear part
+    u64 sumeb[ST_COUNT] = {0, 0, 0};
+    u64 maxeb[ST_COUNT] = {0, 0, 0};
+    u64 segsum[ST_COUNT] = {0, 0, 0};
+    int B = 0;
+    u64 total(const sq_ctx *c) const {
+        u64 t = lin + 64 * 1024;
+        u64 me = 0, ms = 0, mt = 0;
+        for (int s = 0; s < ST_COUNT; s++) {
+            t += 8 * sumeb[s] + 256;
+            me = std::max(me, sumeb[s]);
+            ms = std::max(ms, segsum[s]);
+            mt = std::max(mt, (maxeb[s] + SQ_TILE - 1) / SQ_TILE);
+        }
+        t += 16 * me + 512;                                   // elemA + elemB
+        t += 8 * ms + 256;                                    // seglist
+        t += (u64)B * (1u << SQ_SORT_BITS) * mt * 4 + 256;    // hist
+        t += (u64)B * (sizeof(BlockDesc) + sizeof(BlockState) + 6 * 4 + 8 + 4) + 2048;
+        (void)c;
+        return t;
+    }
+    void add(const sq_ctx *c, const BlkCost &k) {
+        lin += k.inputs + k.perread + k.obuf + k.side + k.rec;
+        u64 nctx[ST_COUNT] = {c->nseq(), c->nqual(), NCTX_NAME};
+        for (int s = 0; s < ST_COUNT; s++) {
+            sumeb[s] += k.eb[s];
+            maxeb[s] = std::max(maxeb[s], k.eb[s]);
+            segsum[s] += std::min<u64>(k.eb[s], nctx[s]);
+        }
+        B++;
+    }
+};
+
+template <class T> T *take(Arena &a, u64 count) { return (T *)a.take(count * sizeof(T)); }
+
+int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, bool host) {
+    cudaStream_t st = c->stream;
+    Arena &A = c->arena;
+    A.reset();
+    EncWave w{};
+    w.B = n; w.nsm = c->nsm;
+    w.md5 = c->p.md5; w.lossy = c->p.lossy; w.id_rule = c->p.id_rule; w.qlevel = c->p.qlevel;
+    w.seqmask = c->nseq() - 1;
+    if (c->p.usemodel) {
+        if (!c->d_model) { c->err = "usemodel = 1 but no snapshot loaded (sq_load_model)"; return SQ_ERR_ARG; }
+        w.snap_name = c->p.id_rule ? nullptr : c->d_model;
+        w.snap_seq = c->d_model + c->snap_name_bytes();
+        w.snap_qual = w.snap_seq + (u64)c->nseq() * 4;
+    }
+    std::vector<BlockDesc> bd(n);
+    std::vector<u32> rbase(n + 1);
+    u64 R = 0;
+    u64 sum[ST_COUNT] = {0, 0, 0}, osum = 0, sidesum = 0, recsum = 0, segsum[ST_COUNT] = {0, 0, 0};
+    u64 nctx[ST_COUNT] = {c->nseq(), c->nqual(), NCTX_NAME};
+    for (int i = 0; i < n; i++) {
+        const sq_block_in &b = blocks[i];
+        BlkCost k = block_cost(c, b, host);
+        BlockDesc &d = bd[i];
+        memset(&d, 0, sizeof d);
+        d.nreads = b.nreads; d.idbytes = b.idbytes; d.seqbytes = b.seqbytes;
+        d.rbase = (u32)R;
+        rbase[i] = (u32)R;
+        R += b.nreads;
+        for (int s = 0; s < ST_COUNT; s++) {
+            d.ebase[s] = sum[s]; d.ebound[s] = k.eb[s];
+            sum[s] += k.eb[s];
+            w.maxbound[s] = std::max(w.maxbound[s], k.eb[s]);
+            segsum[s] += std::min<u64>(k.eb[s], nctx[s]);
+            d.obase[s] = osum; osum += al16(2 * k.eb[s] + 16);
+        }
+        d.sidebase = sidesum; d.sidecap = k.side; sidesum += k.side;
+        d.reccap = k.rec; recsum += k.rec;
+    }
+    rbase[n] = (u32)R;
+    if (R >= 0xffffffffull) { c->err = "too many reads in one wave"; return SQ_ERR_ARG; }
+    w.R = (u32)R;
+
+    // ---- carve the arena
+    bool ok = true;
+    auto need = [&](void *p) { if (!p) ok = false; return p; };
+    w.bd = (BlockDesc *)need(take<BlockDesc>(A, n));
+    w.bs = (BlockState *)need(take<BlockState>(A, n));
+    w.rbase = (u32 *)need(take<u32>(A, n + 1));
+    w.totals = (u32 *)need(take<u32>(A, 6 * (u64)n));
+    w.recoff = (u64 *)need(take<u64>(A, n + 1));
+    w.nseg = (u32 *)need(take<u32>(A, 4));
+    u64 Rr = R ? R : 1;
+    w.seqoff = (u32 *)need(take<u32>(A, Rr)); w.idoff = (u32 *)need(take<u32>(A, Rr));
+    w.acgtoff = (u32 *)need(take<u32>(A, Rr)); w.qlen2 = (u32 *)need(take<u32>(A, Rr));
+    w.qoff = (u32 *)need(take<u32>(A, Rr)); w.noff = (u32 *)need(take<u32>(A, Rr));
+    w.tip = (u8 *)need(take<u8>(A, Rr)); w.np = (u8 *)need(take<u8>(A, Rr)); w.ns = (u8 *)need(take<u8>(A, Rr));
+    u64 maxsum = std::max(sum[0], std::max(sum[1], sum[2]));
+    w.elemA = (u64 *)need(take<u64>(A, maxsum + 1));
+    w.elemB = (u64 *)need(take<u64>(A, maxsum + 1));
+    for (int s = 0; s < ST_COUNT; s++) w.triples[s] = (u64 *)need(take<u64>(A, sum[s] + 1));
+    u64 maxtiles = 0;
+    for (int s = 0; s < ST_COUNT; s++) maxtiles = std::max(maxtiles, (w.maxbound[s] + SQ_TILE - 1) / SQ_TILE);
+    w.hist = (u32 *)need(take<u32>(A, (u64)n * (1u << SQ_SORT_BITS) * maxtiles + 1));
+    u64 segcap = std::max(segsum[0], std::max(segsum[1], segsum[2])) + 1;
+    if (segcap > 0xffffffffull) { c->err = "segment list too large"; return SQ_ERR_ARG; }
+    w.segcap = (u32)segcap;
+    w.seglist = (u64 *)need(take<u64>(A, segcap));
+    w.obuf = (u8 *)need(take<u8>(A, osum + 16));
+    w.sidebuf = (u8 *)need(take<u8>(A, sidesum + 16));
+    if (host) { w.recbuf = (u8 *)need(take<u8>(A, recsum + 16)); w.recbuf_cap = recsum; }
+    // inputs
+    for (int i = 0; i < n && ok; i++) {
+        const sq_block_in &b = blocks[i];
+        BlockDesc &d = bd[i];
+        if (host) {
+            u8 *ids = (u8 *)need(A.take(al16(b.idbytes) + 16));
+            u8 *seq = (u8 *)need(A.take(al16(b.seqbytes) + 16));
+            u8 *qual = (u8 *)need(A.take(al16(b.seqbytes) + 16));
+            u16 *idlen = (u16 *)need(A.take(al16(2ull * b.nreads) + 16));
+            i32 *seqlen = (i32 *)need(A.take(al16(4ull * b.nreads) + 16));
+            d.ids = ids; d.seq = seq; d.qual = qual; d.idlen = idlen; d.seqlen = seqlen;
+        } else {
+            d.ids = b.ids; d.seq = b.seq; d.qual = b.qual; d.idlen = b.idlen; d.seqlen = b.seqlen;
+            d.rec = out[i].data; d.reccap = out[i].cap;
+        }
+        if (c->p.lossy) d.qual_work = (u8 *)need(A.take(al16(b.seqbytes) + 16));
+        else d.qual_work = const_cast<u8 *>(d.qual);
+    }
+    if (!ok) { c->err = "internal: wave does not fit the workspace"; return SQ_ERR_NOMEM; }
+
+    StageTimer &T = c->timer;
+    T.begin(st);
+    if (host) {
+        for (int i = 0; i < n; i++) {
+            const sq_block_in &b = blocks[i];
+            BlockDesc &d = bd[i];
+            if (b.idbytes) CUDA_OK(c, cudaMemcpyAsync((void *)d.ids, b.ids, b.idbytes, cudaMemcpyHostToDevice, st));
+            if (b.seqbytes) {
+                CUDA_OK(c, cudaMemcpyAsync((void *)d.seq, b.seq, b.seqbytes, cudaMemcpyHostToDevice, st));
+                CUDA_OK(c, cudaMemcpyAsync((void *)d.qual, b.qual, b.seqbytes, cudaMemcpyHostToDevice, st));
+            }
+            if (b.nreads) {
+                CUDA_OK(c, cudaMemcpyAsync((void *)d.idlen, b.idlen, 2ull * b.nreads, cudaMemcpyHostToDevice, st));
+                CUDA_OK(c, cudaMemcpyAsync((void *)d.seqlen, b.seqlen, 4ull * b.nreads, cudaMemcpyHostToDevice, st));
+            }
+        }
+    }
+    if (c->p.lossy)
+        for (int i = 0; i < n; i++)
+            if (bd[i].seqbytes) CUDA_OK(c, cudaMemcpyAsync(bd[i].qual_work, bd[i].qual, bd[i].seqbytes, cudaMemcpyDeviceToDevice, st));
+    CUDA_OK(c, cudaMemcpyAsync(w.bd, bd.data(), sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(c, cudaMemcpyAsync(w.rbase, rbase.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
+    CUDA_OK(c, cudaMemsetAsync(w.bs, 0, sizeof(BlockState) * n, st));
+    T.mark("h2d", st);
+
+    u64 *L = &c->launches;
+    CUDA_OK(c, sqk_prep(w, st, L));
+    if (c->p.lossy) { CUDA_OK(c, sqk_rblock(w, c->p.lossy_r, st, L)); T.mark("rblock", st); }
+    CUDA_OK(c, sqk_count(w, st, L));
+    T.mark("count", st);
+    CUDA_OK(c, sqk_md5(w, st, L));
+    T.mark("md5", st);
+    CUDA_OK(c, sqk_side(w, st, L));
+    T.mark("side", st);
+    static const char *nm_emit[3] = {"seq.ctx", "qual.ctx", "name.ctx"};
+    static const char *nm_sort[3] = {"seq.sort", "qual.sort", "name.sort"};
+    static const char *nm_rep[3] = {"seq.replay", "qual.replay", "name.replay"};
+    int keybits[3] = {(int)(2 * c->NS()), c->p.qlevel > 2 ? 20 : 16, 14};
+    for (int s = 0; s < ST_COUNT; s++) {
+        if (s == ST_NAME && c->p.id_rule) continue;
+        CUDA_OK(c, sqk_emit(w, s, w.elemA, st, L));
+        T.mark(nm_emit[s], st);
+        u64 *sorted = nullptr;
+        CUDA_OK(c, sqk_sort(w, s, keybits[s], w.elemA, w.elemB, &sorted, st, L));
+        T.mark(nm_sort[s], st);
+        CUDA_OK(c, sqk_replay(w, s, sorted, w.triples[s], st, L));
+        T.mark(nm_rep[s], st);
+    }
+    CUDA_OK(c, sqk_rc(w, st, L));
+    T.mark("rc", st);
+    CUDA_OK(c, sqk_pack(w, host ? 1 : 0, st, L));
+    T.mark("pack", st);
+
+    // ---- results
+    u64 small = sizeof(BlockState) * (u64)n + 8 * ((u64)n + 1);
+    int rcod = ensure_pin(c, small);
+    if (rcod) return rcod;
+    BlockState *hbs = (BlockState *)c->h_pin;
+    u64 *hoff = (u64 *)(c->h_pin + sizeof(BlockState) * (u64)n);
+    CUDA_OK(c, cudaMemcpyAsync(hbs, w.bs, sizeof(BlockState) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaMemcpyAsync(hoff, w.recoff, 8 * ((u64)n + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    int worst = SQ_OK;
+    for (int i = 0; i < n; i++) {
+        out[i].status = hbs[i].status;
+        out[i].len = hbs[i].reclen;
+        if (hbs[i].status == 0 && host) {
+            if (out[i].len > out[i].cap) out[i].status = SQ_ERR_CAPACITY;
+            else CUDA_OK(c, cudaMemcpyAsync(out[i].data, w.recbuf + hoff[i], out[i].len, cudaMemcpyDeviceToHost, st));
+        }
+        if (out[i].status != 0 && worst == 0) worst = out[i].status;
+    }
+    if (host) { T.mark("d2h", st); CUDA_OK(c, cudaStreamSynchronize(st)); }
+    T.collect();
+    c->last = w; c->last_bd = bd; c->last_valid = true;
+    if (worst) c->err = "one or more blocks failed; see per-block status";
+    return worst;
+}
+
+int encode_blocks(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, bool host) {
+    if (!c || !blocks || !out || n <= 0) { if (c) c->err = "bad argument"; return SQ_ERR_ARG; }
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    for (int i = 0; i < n; i++) {
+        if (blocks[i].longflag) { c->err = "long-read blocks (encode_len_long @0x422e70) are not supported"; return SQ_ERR_ARG; }
+        if (blocks[i].seqbytes >= (1ull << 31) || blocks[i].idbytes >= (1ull << 31)) { c->err = "block too large"; return SQ_ERR_ARG; }
+        if (blocks[i].nreads && (!blocks[i].idlen || !blocks[i].seqlen)) { c->err = "null length array"; return SQ_ERR_ARG; }
+    }
+    c->timer.acc.clear();
+    c->launches = 0;
+    c->last_valid = false;
+    int worst = SQ_OK, i = 0;
+    c->last_wave_blocks = 0;
+    while (i < n) {
+        WaveAcc acc;
+        int j = i;
+        while (j < n) {
+            WaveAcc t = acc;
+            t.add(c, block_cost(c, blocks[j], host));
+            if (t.total(c) > c->arena.cap || t.B > 60000) break;
+            acc = t;
+            j++;
+        }
+        if (j == i) { c->err = "a single block does not fit the device workspace"; return SQ_ERR_NOMEM; }
+        int r = encode_wave(c, blocks + i, j - i, out + i, host);
+        c->last_wave_blocks = std::max(c->last_wave_blocks, j - i);
+        if (r == SQ_ERR_CUDA || r == SQ_ERR_NOMEM || r == SQ_ERR_ARG) return r;
+        if (r && !worst) worst = r;
+        i = j;
+    }
+    return worst;
+}
+
+}  // namespace
+
+extern "C" int sq_encode_blocks(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out) {
+    return encode_blocks(c, blocks, n, out, true);
+}
+extern "C" int sq_encode_blocks_dev(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out) {
+    return encode_blocks(c, blocks, n, out, false);
+}
+
+extern "C" int sq_debug_fetch(sq_ctx *c, int what, int block, void *dst, uint64_t cap, uint64_t *got) {
+    if (!c || !c->last_valid || block < 0 || block >= c->last.B || !dst || !got) return SQ_ERR_ARG;
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    BlockState bs;
+    CUDA_OK(c, cudaMemcpy(&bs, c->last.bs + block, sizeof bs, cudaMemcpyDeviceToHost));
+    if (what == 3) {
+        if (cap < 24) return SQ_ERR_CAPACITY;
+        u64 v[3] = {bs.nsym[0], bs.nsym[1], bs.nsym[2]};
+        memcpy(dst, v, 24);
+        *got = 24;
+        return SQ_OK;
+    }
+    if (what < 0 || what > 2) return SQ_ERR_ARG;
+    u64 bytes = 8ull * bs.nsym[what];
+    if (bytes > cap) return SQ_ERR_CAPACITY;
+    CUDA_OK(c, cudaMemcpy(dst, c->last.triples[what] + c->last_bd[block].ebase[what], bytes, cudaMemcpyDeviceToHost));
+    *got = bytes;
+    return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// R-Block on its own
+extern "C" int sq_rblock(sq_ctx *c, uint8_t *qual, uint64_t n, double r) {
+    if (!c || (!qual && n)) return SQ_ERR_ARG;
+    if (n == 0) return SQ_OK;
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    Arena &A = c->arena;
+    A.reset();
+    c->last_valid = false;
+    BlockDesc d{};
+    BlockDesc *dd = (BlockDesc *)A.take(sizeof d);
+    u8 *q = (u8 *)A.take(n + 16);
+    if (!dd || !q) return SQ_ERR_NOMEM;
+    d.qual_work = q; d.seqbytes = n;
+    EncWave w{};
+    w.B = 1; w.bd = dd;
+    CUDA_OK(c, cudaMemcpyAsync(q, qual, n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(dd, &d, sizeof d, cudaMemcpyHostToDevice, c->stream));
+    u64 l = 0;
+    CUDA_OK(c, sqk_rblock(w, r, c->stream, &l));
+    CUDA_OK(c, cudaMemcpyAsync(qual, q, n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return SQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode
+namespace {
+
+// EBML-style vint (Encap::getValue @0x4207a0): length from the leading 1 bit
+int get_vint(const u8 *p, const u8 *end, u64 *v) {
+    if (p >= end) return 0;
+    int n = 1;
+    u8 m = 0x80;
+    while (n <= 8 && !(p[0] & m)) { n++; m >>= 1; }
+    if (n > 8 || p + n > end) return 0;
+    u64 x = p[0] & (m - 1);
+    for (int i = 1; i < n; i++) x = (x << 8) | p[i];
+    *v = x;
+    return n;
+}
+
+// walk the tags of one block record on the host (doDecode @0x42eb60 loop over doRealDecode cases)
+int parse_record(const sq_ctx *c, const u8 *rec, u64 reclen, DecBlock &d) {
+    const u8 *p = rec, *end = rec + reclen;
+    u64 v;
+    int k = get_vint(p, end, &v);
+    if (!k || v != 1) return SQ_ERR_FORMAT;          // only Fqz blocks (tag 1); Align blocks are out of scope
+    p += k;
+    k = get_vint(p, end, &v);
+    if (!k || p + k + v > end) return SQ_ERR_FORMAT;
+    p += k;
+    end = p + v;
+    bool have_count = false;
+    while (p < end) {
+        u64 tag, sz;
+        k = get_vint(p, end, &tag); if (!k) return SQ_ERR_FORMAT; p += k;
+        k = get_vint(p, end, &sz); if (!k) return SQ_ERR_FORMAT; p += k;
+        if (p + sz > end) return SQ_ERR_FORMAT;
+        const u8 *pay = p;
+        p += sz;
+        if (tag >= 32) continue;
+        if (tag == 1) { if (sz != 4) return SQ_ERR_FORMAT; d.nreads = pay[0] | (pay[1] << 8) | (pay[2] << 16) | ((u32)pay[3] << 24); have_count = true; continue; }
+        int mi = tag == 5 ? 0 : tag == 6 ? 1 : tag == 7 ? 2 : -1;
+        if (mi >= 0 && c->p.md5 && !(mi == 2 && c->p.lossy)) {
+            if (sz < 16) return SQ_ERR_FORMAT;
+            memcpy(d.md5[mi], pay, 16); d.has_md5[mi] = 1;
+            pay += 16; sz -= 16;
+        }
+        if ((tag == 14 || (tag >= 23 && tag <= 26)) && sz < 4) return SQ_ERR_FORMAT;
+        d.off[tag] = (u64)(pay - rec);
+        d.len[tag] = (u32)sz;
+    }
+    if (!have_count) return SQ_ERR_FORMAT;
+    if (d.nreads && (!d.len[4] || !d.len[7] || !d.len[6] || !d.len[5])) return SQ_ERR_FORMAT;
+    return SQ_OK;
+}
+
+u32 rec_count(const u8 *rec, const DecBlock &d, int tag) {
+    if (!d.len[tag]) return 0;
+    const u8 *p = rec + d.off[tag];
+    return p[0] | (p[1] << 8) | (p[2] << 16) | ((u32)p[3] << 24);
+}
+
+int decode_wave(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_block_dec *out, bool host,
+                const std::vector<DecBlock> &parsed) {
+    cudaStream_t st = c->stream;
+    Arena &A = c->arena;
+    A.reset();
+    c->last_valid = false;
+    DecWave w{};
+    w.B = n; w.nsm = c->nsm;
+    w.md5 = c->p.md5; w.lossy = c->p.lossy; w.id_rule = c->p.id_rule; w.qlevel = c->p.qlevel;
+    w.nseq = c->nseq(); w.seqmask = w.nseq - 1; w.nqual = c->nqual();
+    if (c->p.usemodel) {
+        if (!c->d_model) { c->err = "usemodel = 1 but no snapshot loaded (sq_load_model)"; return SQ_ERR_ARG; }
+        w.snap_name = c->p.id_rule ? nullptr : c->d_model;
+        w.snap_seq = c->d_model + c->snap_name_bytes();
+        w.snap_qual = w.snap_seq + (u64)c->nseq() * 4;
+    }
+    std::vector<DecBlock> db(parsed.begin(), parsed.begin() + n);
+    bool ok = true;
+    auto need = [&](void *p) { if (!p) ok = false; return p; };
+    w.db = (DecBlock *)need(take<DecBlock>(A, n));
+    for (int i = 0; i < n && ok; i++) {
+        DecBlock &d = db[i];
+        sq_block_dec &o = out[i];
+        d.idcap = o.idcap; d.seqcap = o.seqcap; d.readcap = o.readcap;
+        if (d.status) continue;
+        if (host) {
+            d.rec = (u8 *)need(A.take(reclens[i] + 16));
+            d.ids = (u8 *)need(A.take(o.idcap + 16));
+            d.seq = (u8 *)need(A.take(o.seqcap + 16));
+            d.qual = (u8 *)need(A.take(o.seqcap + 16));
+            d.idlen = (u16 *)need(A.take(2ull * o.readcap + 16));
+            d.seqlen = (i32 *)need(A.take(4ull * o.readcap + 16));
+        } else {
+            d.rec = recs[i];
+            d.ids = o.ids; d.seq = o.seq; d.qual = o.qual; d.idlen = o.idlen; d.seqlen = o.seqlen;
+        }
+        d.reclen = reclens[i];
+        u64 nr = d.nreads;
+        d.seqoff = (u32 *)need(A.take(4 * (nr + 1) + 16));
+        d.seqtab = (u8 *)need(A.take((u64)w.nseq * 4));
+        d.qualtab = (u32 *)need(A.take((u64)w.nqual * 97 * 4));
+        if (!c->p.id_rule) d.nametab = (u32 *)need(A.take((768ull * 258 + 8192ull * 130) * 4));
+        d.d_tip = (u8 *)need(A.take(nr + 16));
+        d.d_maxq = (u8 *)need(A.take(nr + 16));
+        d.d_cnt = (u32 *)need(A.take(4 * nr + 16));
+        d.d_ch = (u8 *)need(A.take(o.seqcap + 16));
+        d.d_pos = (u32 *)need(A.take(4 * o.seqcap + 16));
+    }
+    if (!ok) { c->err = "internal: decode wave does not fit the workspace"; return SQ_ERR_NOMEM; }
+    StageTimer &T = c->timer;
+    T.begin(st);
+    if (host)
+        for (int i = 0; i < n; i++)
+            if (!db[i].status) CUDA_OK(c, cudaMemcpyAsync((void *)db[i].rec, recs[i], reclens[i], cudaMemcpyHostToDevice, st));
+    CUDA_OK(c, cudaMemcpyAsync(w.db, db.data(), sizeof(DecBlock) * n, cudaMemcpyHostToDevice, st));
+    T.mark("h2d", st);
+    CUDA_OK(c, sqk_decode(w, st, &c->launches));
+    T.mark("decode", st);
+    int rc = ensure_pin(c, sizeof(DecBlock) * (u64)n);
+    if (rc) return rc;
+    DecBlock *hdb = (DecBlock *)c->h_pin;
+    CUDA_OK(c, cudaMemcpyAsync(hdb, w.db, sizeof(DecBlock) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    int worst = SQ_OK;
+    for (int i = 0; i < n; i++) {
+        sq_block_dec &o = out[i];
+        o.status = hdb[i].status; o.nreads = hdb[i].nreads; o.idbytes = hdb[i].idbytes; o.seqbytes = hdb[i].seqbytes;
+        if (o.status == 0 && host) {
+            if (o.idbytes) CUDA_OK(c, cudaMemcpyAsync(o.ids, db[i].ids, o.idbytes, cudaMemcpyDeviceToHost, st));
+            if (o.seqbytes) {
+                CUDA_OK(c, cudaMemcpyAsync(o.seq, db[i].seq, o.seqbytes, cudaMemcpyDeviceToHost, st));
+                CUDA_OK(c, cudaMemcpyAsync(o.qual, db[i].qual, o.seqbytes, cudaMemcpyDeviceToHost, st));
+            }
+            if (o.nreads) {
+                CUDA_OK(c, cudaMemcpyAsync(o.idlen, db[i].idlen, 2ull * o.nreads, cudaMemcpyDeviceToHost, st));
+                CUDA_OK(c, cudaMemcpyAsync(o.seqlen, db[i].seqlen, 4ull * o.nreads, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (o.status && !worst) worst = o.status;
+    }
+    if (host) { T.mark("d2h", st); CUDA_OK(c, cudaStreamSynchronize(st)); }
+    T.collect();
+    if (worst) c->err = "one or more blocks failed to decode; see per-block status";
+    return worst;
+}
+
+u64 dec_block_cost(const sq_ctx *c, u64 reclen, const sq_block_dec &o, u32 nreads, bool host) {
+    u64 t = sizeof(DecBlock) + 20 * 256;
+    if (host) t += reclen + o.idcap + 2 * o.seqcap + 6ull * o.readcap;
+    t += 4ull * (nreads + 1) + (u64)c->nseq() * 4 + (u64)c->nqual() * 97 * 4;
+    if (!c->p.id_rule) t += (768ull * 258 + 8192ull * 130) * 4;
+    t += 6ull * nreads + 5 * o.seqcap;
+    return t;
+}
+
+int decode_blocks(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_block_dec *out, bool host) {
+    if (!c || !recs || !reclens || !out || n <= 0) { if (c) c->err = "bad argument"; return SQ_ERR_ARG; }
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    c->timer.acc.clear();
+    c->launches = 0;
+    c->last_wave_blocks = 0;
+    // parse every record on the host; device-resident records are first copied back (headers are tiny
+    // but scattered, so the whole record is fetched -- the *_dev variant is a measurement aid)
+    std::vector<DecBlock> parsed(n);
+    std::vector<u8> tmp;
+    for (int i = 0; i < n; i++) {
+        memset(&parsed[i], 0, sizeof(DecBlock));
+        const u8 *hp = recs[i];
+        if (!host) {
+            tmp.resize(reclens[i]);
+            CUDA_OK(c, cudaMemcpy(tmp.data(), recs[i], reclens[i], cudaMemcpyDeviceToHost));
+            hp = tmp.data();
+        }
+        int r = parse_record(c, hp, reclens[i], parsed[i]);
+        if (r) parsed[i].status = r;
+        else if (parsed[i].nreads > out[i].readcap) parsed[i].status = SQ_ERR_CAPACITY;
+        else if (rec_count(hp, parsed[i], 14) > out[i].seqcap || rec_count(hp, parsed[i], 26) > out[i].seqcap) parsed[i].status = SQ_ERR_FORMAT;
+    }
+    int worst = SQ_OK, i = 0;
+    while (i < n) {
+        u64 tot = 64 * 1024;
+        int j = i;
+        while (j < n) {
+            u64 k = dec_block_cost(c, reclens[j], out[j], parsed[j].nreads, host);
+            if (tot + k > c->arena.cap) break;
+            tot += k;
+            j++;
+        }
+        if (j == i) { c->err = "a single block does not fit the device workspace"; return SQ_ERR_NOMEM; }
+        std::vector<DecBlock> part(parsed.begin() + i, parsed.begin() + j);
+        int r = decode_wave(c, recs + i, reclens + i, j - i, out + i, host, part);
+        c->last_wave_blocks = std::max(c->last_wave_blocks, j - i);
+        if (r == SQ_ERR_CUDA || r == SQ_ERR_NOMEM || r == SQ_ERR_ARG) return r;
+        if (r && !worst) worst = r;
+        i = j;
+    }
+    return worst;
+}
+
+}  // namespace
+
+extern "C" int sq_decode_blocks(sq_ctx *c, const uint8_t *const *recs, const uint64_t *reclens, int n, sq_block_dec *out) {
+    return decode_blocks(c, recs, reclens, n, out, true);
+}
+extern "C" int sq_decode_blocks_dev(sq_ctx *c, const uint8_t *const *recs, const uint64_t *reclens, int n, sq_block_dec *out) {
+    return decode_blocks(c, recs, reclens, n, out, false);
+}

@@ -1,0 +1,1022 @@
+// sq_encode.cu -- CUDA kernels of the block-united encoder (EncapFqzComp::doFqzEncode @0x42d2d0).
+//
+// Design: on ENCODE every context index is a pure function of the input symbols
+// (seq @0x422090, qual @0x422474-0x422505, name @0x421578-0x4215a4), never of coder state, so a
+// block's encode is decomposed into
+//   1. context kernels      : (context key, symbol, stream position) per coded symbol, coalesced
+//   2. stable radix sort    : group symbols by context inside each block, stream order kept
+//   3. model replay         : one thread per non-empty context replays that context's adaptive
+//                             model over its own symbols and emits (cum, freq, tot) per symbol
+//   4. range-coder pass     : the only serial part -- one warp per (block, stream) runs the
+//                             64-bit low / 32-bit range recurrence over the triples
+//   5. pack                 : tags, sizes, MD5s and side streams are laid out as the block record
+// All kernels work on a WAVE of independent blocks at once (models reset per block).
+#include "sq_common.cuh"
+#include "sq_kernels.h"
+#include "sq_md5.cuh"
+
+#define FULL 0xffffffffu
+
+// =============================================================================================
+// helpers
+SQ_D int find_block(const u32 *rbase, int B, u32 r) {       // rbase[0..B]: first read of each block
+    int lo = 0, hi = B;                                      // invariant rbase[lo] <= r < rbase[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (rbase[mid] <= r) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+SQ_D u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+SQ_D u32 warp_incl_scan(u32 v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(FULL, v, o); if (lane >= o) v += t; }
+    return v;
+}
+
+// =============================================================================================
+// 0. per-read preparation: lengths -> u32 arrays (scanned in place afterwards), validation
+__global__ void k_read_prep(const BlockDesc *bd, BlockState *bs, const u32 *rbase, int B, u32 R,
+                            u32 *seqoff, u32 *idoff) {
+    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= R) return;
+    int b = find_block(rbase, B, w);
+    u32 r = w - rbase[b];
+    i32 sl = bd[b].seqlen[r];
+    u32 il = bd[b].idlen[r];
+    if (sl < 0 || sl > 65535 || il > 255) { bs[b].status = SQ_ERR_INPUT_K; sl = 0; il = 0; }
+    seqoff[w] = (u32)sl;
+    idoff[w] = il;
+}
+
+// the lengths must add up to the buffer sizes the caller gave; a block that fails is skipped by
+// every later kernel (status != 0) so that no kernel reads outside the caller's buffers
+__global__ void k_check_totals(const BlockDesc *bd, BlockState *bs, const u32 *tot_seq, const u32 *tot_id, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (tot_seq[b] != bd[b].seqbytes || tot_id[b] != bd[b].idbytes) bs[b].status = SQ_ERR_INPUT_K;
+}
+
+// In-place exclusive scan of arr[rbase[b] .. rbase[b+1]) for every block b (grid.x = B, grid.y =
+// number of arrays); the block total goes to totals[y * B + b].
+struct ScanArgs { u32 *arr[6]; };
+__global__ void __launch_bounds__(1024) k_excl_scan(ScanArgs a, const u32 *rbase, u32 *totals, int B) {
+    __shared__ u32 wsum[32];
+    __shared__ u32 carry_s;
+    int b = blockIdx.x;
+    u32 *arr = a.arr[blockIdx.y] + rbase[b];
+    u32 n = rbase[b + 1] - rbase[b];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int ITEMS = 8;
+    for (u32 base = 0; base < n; base += 1024 * ITEMS) {
+        u32 v[ITEMS], s = 0;
+        u32 i0 = base + threadIdx.x * ITEMS;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) { v[k] = (i0 + k < n) ? arr[i0 + k] : 0; s += v[k]; }
+        u32 inc = warp_incl_scan(s, lane);
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) { u32 t = wsum[lane]; u32 ti = warp_incl_scan(t, lane); wsum[lane] = ti - t; }
+        __syncthreads();
+        u32 excl = carry_s + wsum[wid] + inc - s;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) { if (i0 + k < n) arr[i0 + k] = excl; excl += v[k]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.y * B + b] = carry_s;
+}
+
+// =============================================================================================
+// 1a. sequence: count coded (ACGT) bases per read / emit (context, base) elements.
+// encode_seq @0x421f30: last = 0x7616c7 & mask at each read start; non-ACGT bases are skipped
+// (@0x421f6d-0x421f7d) and do not enter the context; last = (last*4 + b) & mask (@0x422090).
+template <bool EMIT>
+__global__ void k_seq_pass(const BlockDesc *bd, BlockState *bs, const u32 *rbase, int B, u32 R,
+                           const u32 *seqoff, u32 *acgt, u8 *tip, u64 *elem, u32 mask) {
+    u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= R) return;
+    int b = find_block(rbase, B, w);
+    if (bs[b].status != 0) return;
+    u32 r = w - rbase[b];
+    const u8 *s = bd[b].seq + seqoff[w];
+    u32 len = (u32)bd[b].seqlen[r];
+    u64 prev = 0x7616c7u & mask;
+    u32 done = 0;
+    u32 base = EMIT ? acgt[w] : 0;
+    u64 *dst = EMIT ? elem + bd[b].ebase[ST_SEQ] : nullptr;
+    u32 lt = lanemask_lt();
+    for (u32 i0 = 0; i0 < len; i0 += 32) {
+        u32 i = i0 + lane;
+        u32 v = 4;
+        if (i < len) v = seq_val(s[i]);
+        bool valid = v < 4;
+        u32 bal = __ballot_sync(FULL, valid);
+        u32 cnt = __popc(bal);
+        if (EMIT && cnt) {
+            u32 rk = __popc(bal & lt);
+            // W: the chunk's coded bases, earliest at the top (base with rank j at bits 63-2j..62-2j)
+            u64 x = valid ? ((u64)v << (62 - 2 * rk)) : 0;
+            u32 whi = __reduce_or_sync(FULL, (u32)(x >> 32));
+            u32 wlo = __reduce_or_sync(FULL, (u32)x);
+            u64 W = ((u64)whi << 32) | wlo;
+            if (valid) {
+                u64 h = rk ? ((prev << (2 * rk)) | (W >> (64 - 2 * rk))) : prev;
+                u32 pos = base + done + rk;
+                dst[pos] = el_make((u32)h & mask, v, pos);
+            }
+            prev = (cnt == 32) ? W : ((prev << (2 * cnt)) | (W >> (64 - 2 * cnt)));
+        }
+        done += cnt;
+    }
+    if (!EMIT && lane == 0) {
+        acgt[w] = done;
+        tip[w] = (done != len);
+        if (done != len) atomicAdd(&bs[b].side_cnt[3], 1u);      // flagged reads (= DegeMaxQual count)
+    }
+}
+
+// 1b. quality: encode_qual @0x422180.  COUNT: strip trailing '#' (len2), symbols = len2 + (len2 != len).
+// EMIT: symbol i is coded in context ctx_i = f(q[i-1], q[i-2], q[i-3], delta[i-1]); the optional
+// terminator (symbol 94) is position len2.
+template <bool EMIT>
+__global__ void k_qual_pass(const BlockDesc *bd, BlockState *bs, const u32 *rbase, int B, u32 R,
+                            const u32 *seqoff, u32 *qlen2, u32 *qoff, u64 *elem, int qlevel) {
+    u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= R) return;
+    int b = find_block(rbase, B, w);
+    if (bs[b].status != 0) return;
+    u32 r = w - rbase[b];
+    const u8 *q = bd[b].qual_work + seqoff[w];
+    u32 len = (u32)bd[b].seqlen[r];
+    if (!EMIT) {
+        u32 len2 = 0;
+        bool bad = false;
+        for (u32 i0 = 0; i0 < len; i0 += 32) {
+            u32 i = i0 + lane;
+            u32 c = (i < len) ? q[i] : (u32)'#';
+            if (i < len && (u8)(c - 33) > 94) bad = true;
+            u32 m = __ballot_sync(FULL, c != '#');
+            if (m) len2 = i0 + 32 - __clz(m);
+        }
+        if (__any_sync(FULL, bad) && lane == 0) bs[b].status = SQ_ERR_INPUT_K;
+        if (lane == 0) { qlen2[w] = len2; qoff[w] = len2 + (len2 != len); }
+        return;
+    }
+    u32 len2 = qlen2[w];
+    u32 n2 = len2 + (len2 != len);
+    u32 base = qoff[w];
+    u64 *dst = elem + bd[b].ebase[ST_QUAL];
+    u32 pq1 = 0, pq2 = 0, pq3 = 0;      // q[i0-1], q[i0-2], q[i0-3]
+    u32 pdelta = 5;                      // delta after symbol i0-1
+    for (u32 i0 = 0; i0 < n2; i0 += 32) {
+        u32 i = i0 + lane;
+        u32 sym = 0;
+        if (i < len2) sym = (u8)(q[i] - 33);
+        else if (i < n2) sym = 94;
+        u32 a1 = __shfl_up_sync(FULL, sym, 1), a2 = __shfl_up_sync(FULL, sym, 2), a3 = __shfl_up_sync(FULL, sym, 3);
+        u32 q1 = lane >= 1 ? a1 : pq1;                       // q[i-1]
+        u32 q2 = lane >= 2 ? a2 : (lane == 1 ? pq1 : pq2);   // q[i-2]
+        u32 q3 = lane >= 3 ? a3 : (lane == 2 ? pq1 : (lane == 1 ? pq2 : pq3));   // q[i-3]
+        u32 d = (i < len2 && q1 > sym) ? q1 - sym : 0;       // delta += (q1 > q) * (q1 - q)
+        u32 dinc = warp_incl_scan(d, lane);
+        u32 delta_i = pdelta + dinc;                         // delta after symbol i
+        u32 dprev = __shfl_up_sync(FULL, delta_i, 1);
+        if (lane == 0) dprev = pdelta;                       // delta after symbol i-1
+        if (i < n2) {
+            u32 ctx = (i == 0) ? 0 : qual_ctx(q1, q2, q3, dprev, qlevel, (int)i - 1);
+            dst[base + i] = el_make(ctx, sym, base + i);
+        }
+        pq3 = __shfl_sync(FULL, sym, 29); pq2 = __shfl_sync(FULL, sym, 30); pq1 = __shfl_sync(FULL, sym, 31);
+        pdelta = __shfl_sync(FULL, delta_i, 31);
+    }
+}
+
+// 1c. names: encode_name @0x421070 (fqzcomp nlevel-1 name model).  The model
+// contexts depend on the previous name only, so every read is independent given the input.
+// last_name[] is never cleared in the reference (memcpy of the new name over the old one,
+// @0x42452c): index j >= the previous length still holds the most recent earlier name that was
+// longer than j, or ' ' from the per-block reset.
+struct NameView {
+    const u8 *ids; const u16 *idlen; const u32 *idoff;   // block-relative arrays of this block
+    u32 r;                                               // current read
+    SQ_D u32 last(int j) const {
+        if (j < 0) return 0;                             // byte in front of last_name[] (@+0x1087) is 0
+        for (i64 rr = (i64)r - 1; rr >= 0; rr--)
+            if ((int)idlen[rr] > j) return ids[idoff[rr] + j];
+        return ' ';
+    }
+};
+
+template <bool EMIT>
+__global__ void k_name_pass(const BlockDesc *bd, BlockState *bs, const u32 *rbase, int B, u32 R,
+                            const u32 *idoff, u8 *np, u8 *ns, u32 *noff, u64 *elem) {
+    u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= R) return;
+    int b = find_block(rbase, B, w);
+    if (bs[b].status != 0) return;
+    u32 r = w - rbase[b];
+    NameView nv{bd[b].ids, bd[b].idlen, idoff + rbase[b], r};
+    const u8 *name = nv.ids + nv.idoff[r];
+    int n = nv.idlen[r];
+    int lnl = r ? (int)nv.idlen[r - 1] : 0;
+    int p, s;
+    if (!EMIT) {
+        p = 0; s = 0;
+        if (n > 0 && lnl > 0) {
+            const u8 *last = nv.ids + nv.idoff[r - 1];
+            if (name[0] == last[0]) { p = 1; while (p < n && p < lnl && name[p] == last[p]) p++; }
+            int i = n - 1, j = lnl - 1;
+            while (i >= 0 && j >= 0 && name[i] == last[j]) { i--; j--; }
+            s = n - 1 - i;
+        }
+        if (n - s - p < 0) s = n - p;
+        np[w] = (u8)p; ns[w] = (u8)s;
+        noff[w] = 3 + (u32)(n - s - p);
+        return;
+    }
+    p = np[w]; s = ns[w];
+    u32 o = noff[w];
+    u64 *dst = elem + bd[b].ebase[ST_NAME];
+    u32 lpl = r ? np[w - 1] : 0, lsl = r ? ns[w - 1] : 0;
+    dst[o] = el_make(NK_PREFIX + lpl, (u32)p, o); o++;
+    dst[o] = el_make(NK_SUFFIX + lsl, (u32)s, o); o++;
+    dst[o] = el_make(NK_LEN + (u32)lnl, (u32)n, o); o++;
+    int len2 = n - s, lc2 = (p != 0), i = p, j = p, k = 0;
+    bool bad = false;
+    while (i < len2) {
+        u32 lj = nv.last(j);
+        int v = ((int)lj - 32) * 2 + lc2 + k * 64;
+        int ctx = v % 8192;
+        if (ctx < 0) { bad = true; ctx = 0; }
+        u32 ch = name[i];
+        dst[o] = el_make(NK_MIDDLE + (u32)ctx, ch & 0x7f, o); o++;
+        if (ch == ' ' && nv.last(j) != ' ') j++;
+        if (ch != ' ' && nv.last(j) == ' ') j--;
+        if (ch == ':' && nv.last(j) != ':') j++;
+        if (ch != ':' && nv.last(j) == ':') j--;
+        if (ch == ':' || ch == ' ') k = (k + 3) & ~3;
+        if (j < 0) { j = 0; lc2 = 0; }
+        else { lc2 = (ch == nv.last(j)); j++; }
+        k++; i++;
+    }
+    if (bad) bs[b].status = SQ_ERR_INPUT_K;
+}
+
+// record the per-stream symbol counts (totals of the scans) in BlockState
+__global__ void k_set_counts(BlockState *bs, const u32 *totals, int B, int with_names) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    // totals layout: [y * B + b]; y = 0 acgt, 1 qual symbols, 2 name symbols
+    bool okb = bs[b].status == 0;
+    bs[b].nsym[ST_SEQ] = okb ? totals[0 * B + b] : 0;
+    bs[b].acgt = bs[b].nsym[ST_SEQ];
+    bs[b].nsym[ST_QUAL] = okb ? totals[1 * B + b] : 0;
+    bs[b].nsym[ST_NAME] = (okb && with_names) ? totals[2 * B + b] : 0;
+}
+
+// =============================================================================================
+// 2. stable LSD radix sort by context key, segmented per block.  One warp owns one tile of
+// SQ_TILE consecutive elements; digit ranks come from __match_any_sync so any key skew costs the same.
+// hist layout per block: [digit][tile] (tile-minor), block stride = D * maxtiles.
+template <int BITS>
+__global__ void __launch_bounds__(SQ_SORT_THREADS) k_sort_hist(const u64 *src, u32 *hist, const BlockDesc *bd,
+                                                               const BlockState *bs, int stream, int shift, u32 maxtiles) {
+    constexpr int D = 1 << BITS;
+    extern __shared__ u32 smem[];
+    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u32 *cnt = smem + wid * D;
+    int b = blockIdx.y;
+    u32 tile = blockIdx.x * (SQ_SORT_THREADS / 32) + wid;
+    if (tile >= maxtiles) return;
+    for (int d = lane; d < D; d += 32) cnt[d] = 0;
+    __syncwarp();
+    u32 n = bs[b].nsym[stream];
+    u64 t0 = (u64)tile * SQ_TILE;
+    if (t0 < n) {
+        u32 m = (u32)min((u64)SQ_TILE, (u64)n - t0);
+        const u64 *p = src + bd[b].ebase[stream] + t0;
+        for (u32 i0 = 0; i0 < m; i0 += 32) {
+            u32 i = i0 + lane;
+            bool valid = i < m;
+            u32 act = __ballot_sync(FULL, valid);
+            if (valid) {
+                u32 dg = (u32)(p[i] >> (40 + shift)) & (D - 1);
+                u32 peers = __match_any_sync(act, dg);
+                if ((peers & lanemask_lt()) == 0) cnt[dg] += __popc(peers);
+            }
+            __syncwarp();
+        }
+    }
+    u32 *h = hist + (u64)b * D * maxtiles + tile;
+    for (int d = lane; d < D; d += 32) h[(u64)d * maxtiles] = cnt[d];
+}
+
+// exclusive scan of one block's [digit][tile] histogram (grid.x = B)
+__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, u64 entries_per_block) {
+    __shared__ u32 wsum[32];
+    u32 *h = hist + (u64)blockIdx.x * entries_per_block;
+    u64 per = (entries_per_block + 1023) / 1024;
+    u64 lo = min(entries_per_block, (u64)threadIdx.x * per), hi = min(entries_per_block, lo + per);
+    u32 s = 0;
+    for (u64 i = lo; i < hi; i++) s += h[i];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 inc = warp_incl_scan(s, lane);
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) { u32 t = wsum[lane]; u32 ti = warp_incl_scan(t, lane); wsum[lane] = ti - t; }
+    __syncthreads();
+    u32 run = wsum[wid] + inc - s;
+    for (u64 i = lo; i < hi; i++) { u32 t = h[i]; h[i] = run; run += t; }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(SQ_SORT_THREADS) k_sort_scatter(const u64 *src, u64 *dst, const u32 *hist, const BlockDesc *bd,
+                                                                  const BlockState *bs, int stream, int shift, u32 maxtiles) {
+    constexpr int D = 1 << BITS;
+    extern __shared__ u32 smem[];
+    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u32 *cur = smem + wid * D;
+    int b = blockIdx.y;
+    u32 tile = blockIdx.x * (SQ_SORT_THREADS / 32) + wid;
+    if (tile >= maxtiles) return;
+    u32 n = bs[b].nsym[stream];
+    u64 t0 = (u64)tile * SQ_TILE;
+    if (t0 >= n) return;
+    const u32 *h = hist + (u64)b * D * maxtiles + tile;
+    for (int d = lane; d < D; d += 32) cur[d] = h[(u64)d * maxtiles];
+    __syncwarp();
+    u32 m = (u32)min((u64)SQ_TILE, (u64)n - t0);
+    const u64 *p = src + bd[b].ebase[stream] + t0;
+    u64 *q = dst + bd[b].ebase[stream];
+    u32 lt = lanemask_lt();
+    for (u32 i0 = 0; i0 < m; i0 += 32) {
+        u32 i = i0 + lane;
+        bool valid = i < m;
+        u32 act = __ballot_sync(FULL, valid);
+        if (valid) {
+            u64 e = p[i];
+            u32 dg = (u32)(e >> (40 + shift)) & (D - 1);
+            u32 peers = __match_any_sync(act, dg);
+            u32 rk = __popc(peers & lt);
+            u32 off = cur[dg];
+            __syncwarp(act);
+            if (rk == 0) cur[dg] = off + __popc(peers);
+            q[off + rk] = e;
+        }
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
+// 3a. list of context segments (heads) of the sorted element array
+__global__ void k_seglist(const u64 *src, const BlockDesc *bd, const BlockState *bs, int stream,
+                          u64 *seglist, u32 *nseg, u32 segcap) {
+    int b = blockIdx.y;
+    u32 n = bs[b].nsym[stream];
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    if ((i & ~31u) >= n) return;
+    u64 g = bd[b].ebase[stream] + i;
+    bool head = false;
+    if (i < n) head = (i == 0) || (el_key(src[g - 1]) != el_key(src[g]));
+    u32 bal = __ballot_sync(FULL, head);
+    if (!bal) return;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(nseg, (u32)__popc(bal));
+    base = __shfl_sync(FULL, base, 0);
+    if (head) {
+        u32 slot = base + __popc(bal & lanemask_lt());
+        if (slot < segcap) seglist[slot] = ((u64)b << 40) | g;
+    }
+}
+
+// warp-granular dynamic work distribution over the segment list
+SQ_D u32 grab32(u32 *cursor, int lane) {
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(cursor, 32u);
+    return __shfl_sync(FULL, base, 0);
+}
+
+// 3b. base model replay (fqzcomp BASE_MODEL<uint8_t>, @0x421f7f-0x422087): 4 byte counters per
+// context, init 3 (or the snapshot's table), halve when the sum exceeds 253 BEFORE coding.
+__global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockDesc *bd, const BlockState *bs,
+                                                    const u64 *seglist, const u32 *nseg, u32 *cursor,
+                                                    u64 *triples, const u8 *snap_seq) {
+    int lane = threadIdx.x & 31;
+    u32 total = *nseg;
+    for (;;) {
+        u32 base = grab32(cursor, lane);
+        if (base >= total) break;
+        u32 idx = base + lane;
+        if (idx >= total) continue;
+        u64 ent = seglist[idx];
+        int b = (int)(ent >> 40);
+        u64 g = ent & (((u64)1 << 40) - 1);
+        u64 eb = bd[b].ebase[ST_SEQ];
+        u64 end = eb + bs[b].nsym[ST_SEQ];
+        u64 e = src[g];
+        u32 key = el_key(e);
+        u32 S0 = 3, S1 = 3, S2 = 3, S3 = 3;
+        if (snap_seq) { const u8 *t = snap_seq + (u64)key * 4; S0 = t[0]; S1 = t[1]; S2 = t[2]; S3 = t[3]; }
+        u64 *out = triples + eb;
+        for (;;) {
+            u32 sym = el_sym(e);
+            u32 tot = S0 + S1 + S2 + S3;
+            if (tot > 253) {
+                S0 -= S0 >> 1; S1 -= S1 >> 1; S2 -= S2 >> 1; S3 -= S3 >> 1;
+                tot = S0 + S1 + S2 + S3;
+            }
+            u32 cum, f;
+            if (sym == 0) { cum = 0; f = S0; S0 = (S0 + 1) & 0xff; }
+            else if (sym == 1) { cum = S0; f = S1; S1 = (S1 + 1) & 0xff; }
+            else if (sym == 2) { cum = S0 + S1; f = S2; S2 = (S2 + 1) & 0xff; }
+            else { cum = S0 + S1 + S2; f = S3; S3 = (S3 + 1) & 0xff; }
+            out[el_pos(e)] = tr_make(cum, f, tot);
+            if (++g >= end) break;
+            e = src[g];
+            if (el_key(e) != key) break;
+        }
+    }
+}
+
+// 3c. SIMPLE_MODEL<N> replay (encodeSymbol @0x4221fb-0x4222f1).  The model of the thread's
+// context lives in shared memory, transposed (word w of thread t at w*BD + t) so that every lane
+// always hits its own bank.  keylo/keyhi select which contexts this launch handles; snap (may be
+// null) + snapstride give the packed snapshot model of key `keylo + k` at snap + k*snapstride.
+template <int N, int BD>
+__global__ void __launch_bounds__(BD) k_replay_sm(const u64 *src, const BlockDesc *bd, const BlockState *bs, int stream,
+                                                  const u64 *seglist, const u32 *nseg, u32 *cursor, u64 *triples,
+                                                  u32 keylo, u32 keyhi, const u8 *snap, u32 snapstride) {
+    extern __shared__ u32 smem[];
+    u32 *F = smem + threadIdx.x;                 // F[k] at F[k * BD]
+    int lane = threadIdx.x & 31;
+    u32 total = *nseg;
+    for (;;) {
+        u32 base = grab32(cursor, lane);
+        if (base >= total) break;
+        u32 idx = base + lane;
+        if (idx >= total) continue;
+        u64 ent = seglist[idx];
+        int b = (int)(ent >> 40);
+        u64 g = ent & (((u64)1 << 40) - 1);
+        u64 e = src[g];
+        u32 key = el_key(e);
+        if (key < keylo || key >= keyhi) continue;
+        u64 eb = bd[b].ebase[stream];
+        u64 end = eb + bs[b].nsym[stream];
+        u32 tot, bub;
+        if (snap) {
+            const u8 *s = snap + (u64)(key - keylo) * snapstride;
+            tot = get_u32le(s); bub = get_u32le(s + 4);
+            s += 8;
+            for (int k = 0; k < N; k++, s += 3) F[k * BD] = (u32)s[0] | ((u32)(s[1] | (s[2] << 8)) << 16);
+        } else {
+            tot = N; bub = 0;
+            for (int k = 0; k < N; k++) F[k * BD] = (u32)k | (1u << 16);
+        }
+        u64 *out = triples + eb;
+        for (;;) {
+            u32 sym = el_sym(e);
+            u32 cum = 0;
+            int k = 0;
+            u32 fk = F[0];
+            while ((fk & 0xffffu) != sym && k < N - 1) { cum += fk >> 16; k++; fk = F[k * BD]; }
+            u32 f = fk >> 16;
+            out[el_pos(e)] = tr_make(cum, f, tot);
+            f += 8; tot += 8;
+            fk = (fk & 0xffffu) | (f << 16);
+            F[k * BD] = fk;
+            if (tot > 0xffe0u) {
+                tot = 0;
+                for (int j = 0; j < N; j++) {
+                    u32 x = F[j * BD], gq = x >> 16;
+                    gq -= gq >> 1;
+                    F[j * BD] = (x & 0xffffu) | (gq << 16);
+                    tot += gq;
+                }
+                fk = F[k * BD];
+            }
+            if (((++bub) & 15) == 0 && k > 0) {
+                u32 pk = F[(k - 1) * BD];
+                if ((fk >> 16) > (pk >> 16)) { F[k * BD] = pk; F[(k - 1) * BD] = fk; }
+            }
+            if (++g >= end) break;
+            e = src[g];
+            if (el_key(e) != key) break;
+        }
+    }
+}
+
+// =============================================================================================
+// 4. range-coder pass: one warp per (block, stream).  Lanes fetch 32 triples coalesced and turn
+// each `tot` into a multiply-shift divisor in parallel; lane 0 then runs the serial recurrence
+// (RangeCoder::Encode @0x422010-0x422085) over the 32 prepared records and emits bytes.
+__global__ void __launch_bounds__(32) k_rc(const BlockDesc *bd, BlockState *bs, const u64 *tr_seq, const u64 *tr_qual,
+                                           const u64 *tr_name, u8 *obuf, int skip_name) {
+    __shared__ uint4 rec[2][32];
+    int b = blockIdx.x, st = blockIdx.y, lane = threadIdx.x;
+    if (st == ST_NAME && skip_name) return;
+    const u64 *tr = (st == ST_SEQ ? tr_seq : st == ST_QUAL ? tr_qual : tr_name) + bd[b].ebase[st];
+    u32 n = bs[b].nsym[st];
+    u8 *out = obuf + bd[b].obase[st];
+    u64 low = 0;
+    u32 range = 0xffffffffu;
+    u32 nout = 0;
+    u64 t = (lane < n) ? tr[lane] : 0;
+    int pp = 0;
+    for (u32 base = 0; base < n; base += 32, pp ^= 1) {
+        u32 cnt = min(32u, n - base);
+        if ((u32)lane < cnt) {
+            u32 tot = (u32)(t >> 32) & 0xffffu;
+            FastDiv fd = fastdiv_make(tot < 2 ? 2 : tot);
+            rec[pp][lane] = make_uint4(fd.m, fd.sh, (u32)t & 0xffffu, (u32)(t >> 16) & 0xffffu);
+        }
+        u32 nx = base + 32 + lane;
+        t = (nx < n) ? tr[nx] : 0;                  // prefetch the next 32 while lane 0 codes
+        __syncwarp();
+        if (lane == 0) {
+            for (u32 j = 0; j < cnt; j++) {
+                uint4 rr = rec[pp][j];
+                u32 tt = __umulhi(rr.x, range);
+                u32 q = (tt + ((range - tt) >> 1)) >> rr.y;
+                low += (u32)(rr.z * q);
+                range = q * rr.w;
+                while (range < (1u << 24)) {
+                    if ((low ^ (low + range)) >> 56) range = (((u32)low) | 0xffffffu) - (u32)low;
+                    out[nout++] = (u8)(low >> 56);
+                    range <<= 8;
+                    low <<= 8;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (int i = 0; i < 8; i++) { out[nout++] = (u8)(low >> 56); low <<= 8; }
+        bs[b].olen[st] = nout;
+    }
+}
+
+// =============================================================================================
+// MD5 of the three input buffers of a block (calcBlockMd5 @0x414d90): one thread per buffer.
+__global__ void __launch_bounds__(32) k_md5(const BlockDesc *bd, BlockState *bs, int B) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * B) return;
+    int b = t / 3, which = t % 3;
+    const u8 *p = which == 0 ? bd[b].ids : which == 1 ? bd[b].seq : bd[b].qual;
+    u64 n = which == 0 ? bd[b].idbytes : bd[b].seqbytes;
+    md5_buffer(p, n, bs[b].md5[which]);
+}
+
+// =============================================================================================
+// R-Block lossy smoothing (EncapFqzComp::rblock @0x426c10): greedy runs over the
+// block's concatenated quality bytes, end of data = byte count.  Serial per
+// block; doubles exactly as the reference (IEEE sqrt / div, round half up).
+SQ_D double rnd_half_up(double x) { return floor(x + 0.5); }
+__global__ void __launch_bounds__(32) k_rblock(const BlockDesc *bd, int B, double r) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    u8 *q = bd[b].qual_work;
+    u64 n = bd[b].seqbytes;
+    if (n == 0) return;
+    u64 start = 0, i = 1;
+    int mn = q[0], mx = q[0];
+    for (;;) {
+        bool close = false;
+        int ch = 0;
+        if (i >= n) close = true;
+        else {
+            ch = q[i];
+            if (ch >= mn && ch <= mx) { i++; continue; }
+            if (ch > mx) {
+                double g = rnd_half_up(sqrt((double)ch * mn));
+                if (r > g / mn && r > ch / g) { mx = ch; i++; continue; }
+            } else {
+                double g = rnd_half_up(sqrt((double)ch * mx));
+                if (r > g / ch && r > mx / g) { mn = ch; i++; continue; }
+            }
+            close = true;
+        }
+        if (close) {
+            u8 v = (u8)rnd_half_up(sqrt((double)mn * mx));
+            for (u64 k = start; k < i; k++) q[k] = v;
+            if (i >= n) return;
+            start = i; mn = mx = ch; i++;
+        }
+    }
+}
+
+// =============================================================================================
+// Side streams: Len (compressLen @0x424120 / encode_len_short @0x4239a0), DegeTip / DegeCh /
+// DegeMaxQual (@0x424dd0 / @0x425080 / @0x425310, arrays of DegeInfoProcess @0x433a10) and
+// NDegeCnt / NDegePos (kModel @0x42cbe0 / @0x42ccb0, @0x42d010 / @0x42d170).  KB-scale, serial:
+// one warp (lane 0) per stream, five warps per block.
+struct KModel {
+    SmModel<64> nb;
+    SmModel<2> bits[64];
+    SQ_D void init() { nb.init(); for (int i = 0; i < 64; i++) bits[i].init(); }
+    SQ_D void encode(RcEnc &rc, u32 v) {
+        int n = 32 - __clz(v | 0) ; if (v == 0) n = 0;
+        nb.encode(rc, (u32)n);
+        for (int i = 0; i < n; i++) bits[i].encode(rc, (v >> i) & 1);
+    }
+};
+struct SideSmem {
+    SmModel<256> len1, len2;
+    SmModel<2> same, tip;
+    SmModel<11> ch;
+    SmModel<95> maxq;
+    KModel km;
+    u64 off[7];
+};
+
+__global__ void __launch_bounds__(160) k_side(const BlockDesc *bd, BlockState *bs, const u32 *rbase,
+                                              const u32 *seqoff, const u8 *tip, u8 *sidebuf) {
+    __shared__ SideSmem sm;
+    int b = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BlockDesc &d = bd[b];
+    if (bs[b].status != 0) return;
+    u32 n = d.nreads;
+    u32 nch = (u32)d.seqbytes - bs[b].acgt;
+    u32 nf = bs[b].side_cnt[3];
+    if (threadIdx.x == 0) {
+        // scratch regions: Len, Tip, Ch, MaxQ, Cnt, Pos (generous; overflow is detected, not assumed away)
+        u64 o = 0;
+        sm.off[0] = o; o += 6ull * n + 16;
+        sm.off[1] = o; o += 2ull * n + 16;
+        sm.off[2] = o; o += 2ull * nch + 16;
+        sm.off[3] = o; o += 2ull * nf + 16;
+        sm.off[4] = o; o += 8ull * nf + 16;
+        sm.off[5] = o;
+        sm.off[6] = d.sidecap;
+        if (o + 16 > d.sidecap) { bs[b].status = SQ_ERR_CAPACITY_K; for (int k = 0; k < 6; k++) sm.off[k] = 0; sm.off[6] = 0; }
+    }
+    __syncthreads();
+    if (lane != 0) return;
+    u8 *base = sidebuf + d.sidebase;
+    const u32 *so = seqoff + rbase[b];
+    const u8 *tp = tip + rbase[b];
+    RcEnc rc;
+    int ovf = 0;
+    if (wid == 0) {                                             // Len
+        rc.start(base + sm.off[0], base + sm.off[1]);
+        sm.len1.init(); sm.len2.init(); sm.same.init();
+        for (u32 r = 0; r < n; r++) {
+            i32 len = d.seqlen[r];
+            // the encoder compares with this+0x1060, which it never writes (ctor value 0): SURVEY 8a quirk
+            if (len != 0) { sm.same.encode(rc, 0); sm.len1.encode(rc, len & 0xff); sm.len2.encode(rc, (len >> 8) & 0xff); }
+            else sm.same.encode(rc, 1);
+        }
+        rc.finish();
+        bs[b].side_len[0] = (u32)(rc.out - (base + sm.off[0])); bs[b].side_cnt[0] = n; ovf = rc.overflow;
+    } else if (wid == 1) {                                      // DegeTip: per-read has-non-ACGT flag
+        rc.start(base + sm.off[1], base + sm.off[2]);
+        sm.tip.init();
+        for (u32 r = 0; r < n; r++) sm.tip.encode(rc, tp[r]);
+        rc.finish();
+        bs[b].side_len[1] = (u32)(rc.out - (base + sm.off[1])); bs[b].side_cnt[1] = n; ovf = rc.overflow;
+    } else if (wid == 2) {                                      // DegeCh: the non-ACGT characters
+        rc.start(base + sm.off[2], base + sm.off[3]);
+        sm.ch.init();
+        u32 cnt = 0;
+        for (u32 r = 0; r < n; r++) {
+            if (!tp[r]) continue;
+            const u8 *s = d.seq + so[r];
+            u32 len = (u32)d.seqlen[r];
+            for (u32 i = 0; i < len; i++) { u32 v = seq_val(s[i]); if (v > 3) { sm.ch.encode(rc, v - 4); cnt++; } }
+        }
+        rc.finish();
+        bs[b].side_len[2] = (u32)(rc.out - (base + sm.off[2])); bs[b].side_cnt[2] = cnt; ovf = rc.overflow;
+    } else if (wid == 3) {                                      // DegeMaxQual
+        rc.start(base + sm.off[3], base + sm.off[4]);
+        sm.maxq.init();
+        for (u32 r = 0; r < n; r++) {
+            if (!tp[r]) continue;
+            const u8 *s = d.seq + so[r], *q = d.qual + so[r];
+            u32 len = (u32)d.seqlen[r];
+            u8 mq = 0;
+            for (u32 i = 0; i < len; i++) if (seq_val(s[i]) > 3 && (int)(int8_t)q[i] > (int)mq) mq = q[i];
+            sm.maxq.encode(rc, (u32)(u16)(mq - 33));
+        }
+        rc.finish();
+        bs[b].side_len[3] = (u32)(rc.out - (base + sm.off[3])); ovf = rc.overflow;   // side_cnt[3] = nf already
+    } else if (wid == 4) {                                      // NDegeCnt then NDegePos (shared kModel)
+        sm.km.init();
+        rc.start(base + sm.off[4], base + sm.off[5]);
+        u32 npos = 0;
+        for (u32 r = 0; r < n; r++) {
+            if (!tp[r]) continue;
+            const u8 *s = d.seq + so[r], *q = d.qual + so[r];
+            u32 len = (u32)d.seqlen[r];
+            u8 mq = 0;
+            for (u32 i = 0; i < len; i++) if (seq_val(s[i]) > 3 && (int)(int8_t)q[i] > (int)mq) mq = q[i];
+            u32 c = 0;
+            for (u32 i = 0; i < len; i++) if (!((int)mq < (int)(int8_t)q[i]) && seq_val(s[i]) <= 3) c++;
+            sm.km.encode(rc, c);
+            npos += c;
+        }
+        rc.finish();
+        bs[b].side_len[4] = (u32)(rc.out - (base + sm.off[4])); bs[b].side_cnt[4] = nf; ovf = rc.overflow;
+        rc.start(base + sm.off[5], base + sm.off[6]);
+        for (u32 r = 0; r < n; r++) {
+            if (!tp[r]) continue;
+            const u8 *s = d.seq + so[r], *q = d.qual + so[r];
+            u32 len = (u32)d.seqlen[r];
+            u8 mq = 0;
+            for (u32 i = 0; i < len; i++) if (seq_val(s[i]) > 3 && (int)(int8_t)q[i] > (int)mq) mq = q[i];
+            u32 gap = 0;
+            for (u32 i = 0; i < len; i++) {
+                if ((int)mq < (int)(int8_t)q[i]) continue;
+                if (seq_val(s[i]) > 3) gap++;
+                else { sm.km.encode(rc, gap); gap = 0; }
+            }
+        }
+        rc.finish();
+        bs[b].side_len[5] = (u32)(rc.out - (base + sm.off[5])); bs[b].side_cnt[5] = npos; ovf |= rc.overflow;
+    }
+    if (ovf) bs[b].status = SQ_ERR_CAPACITY_K;
+}
+
+// =============================================================================================
+// 5. pack: block record "tag 1 | size(4) | count | Len | ID | Qual | Dege* | Seq" (SURVEY App. A;
+// doFqzEncode @0x42d2d0).  k_layout sizes the records (and, for the compact wave buffer, assigns
+// offsets by a scan over blocks); k_pack copies the pieces.
+struct PackCfg { int md5, lossy, id_rule; };
+__constant__ int c_side_tag[6] = {4, 23, 14, 24, 25, 26};
+
+SQ_D u32 id_payload_len(const BlockDesc &d, const BlockState &s, PackCfg cfg) {
+    u32 x = cfg.md5 ? 16 : 0;
+    if (cfg.id_rule) x += 2 + (d.nreads ? (u32)d.idlen[0] : 0);      // IDProcess::encodeIDS @0x430040
+    else x += s.olen[ST_NAME];
+    return x;
+}
+SQ_D u32 record_len(const BlockDesc &d, const BlockState &s, PackCfg cfg) {
+    u32 x = 5 + 6;                                                    // tag 1 + size4, count record
+    x += 5 + s.side_len[0];                                           // Len
+    x += 5 + id_payload_len(d, s, cfg);
+    x += 5 + ((cfg.md5 && !cfg.lossy) ? 16 : 0) + s.olen[ST_QUAL];
+    for (int k = 1; k < 6; k++) if (s.side_cnt[k]) x += 5 + 4 + s.side_len[k];
+    x += 5 + (cfg.md5 ? 16 : 0) + s.olen[ST_SEQ];
+    return x;
+}
+
+// single CTA: lengths and (when compact != 0) consecutive offsets into recbuf
+__global__ void __launch_bounds__(1024) k_layout(BlockDesc *bd, BlockState *bs, int B, PackCfg cfg, u8 *recbuf,
+                                                 u64 recbuf_cap, u64 *recoff, int compact) {
+    __shared__ u64 carry;
+    __shared__ u64 wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < B; b0 += 1024) {
+        int b = b0 + threadIdx.x;
+        u64 len = 0;
+        if (b < B) { len = record_len(bd[b], bs[b], cfg); bs[b].reclen = (u32)len; }
+        u64 inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            u64 t = wsum[lane], ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { u64 u = __shfl_up_sync(FULL, ti, o); if (lane >= o) ti += u; }
+            wsum[lane] = ti - t;
+        }
+        __syncthreads();
+        u64 off = carry + wsum[wid] + inc - len;
+        if (b < B) {
+            recoff[b] = off;
+            if (compact) {
+                bd[b].rec = recbuf + off;
+                bd[b].reccap = off + len <= recbuf_cap ? len : 0;
+            }
+            if (len > bd[b].reccap && bs[b].status == 0) bs[b].status = SQ_ERR_CAPACITY_K;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = off + len;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) recoff[B] = carry;
+}
+
+SQ_D void copy_bytes(u8 *dst, const u8 *src, u32 n, u32 tid, u32 nthr) {
+    for (u32 i = tid; i < n; i += nthr) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) k_pack(const BlockDesc *bd, const BlockState *bs, PackCfg cfg,
+                                              const u8 *obuf, const u8 *sidebuf) {
+    int b = blockIdx.y;
+    const BlockDesc &d = bd[b];
+    const BlockState &s = bs[b];
+    if (s.status != 0) return;
+    u8 *rec = d.rec;
+    u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    u32 p = 0;
+    bool w0 = (tid == 0);
+    // tag 1 + size of everything after the size slot
+    if (w0) { put_tag(rec, 1); put_size4(rec + 1, s.reclen - 5); }
+    p = 5;
+    if (w0) { rec[p] = 0x81; rec[p + 1] = 0x84; put_u32le(rec + p + 2, d.nreads); }   // compressCount @0x422a00
+    p += 6;
+    // Len (tag 4): pure range-coder bytes
+    if (w0) { put_tag(rec + p, 4); put_size4(rec + p + 1, s.side_len[0]); }
+    p += 5;
+    copy_bytes(rec + p, sidebuf + d.sidebase, s.side_len[0], tid, nthr);   // Len region is at offset 0
+    p += s.side_len[0];
+    // ID (tag 5)
+    u32 idl = id_payload_len(d, s, cfg);
+    if (w0) { put_tag(rec + p, 5); put_size4(rec + p + 1, idl); }
+    p += 5;
+    if (cfg.md5) { copy_bytes(rec + p, s.md5[0], 16, tid, nthr); p += 16; }
+    if (cfg.id_rule) {
+        u32 l = d.nreads ? (u32)d.idlen[0] : 0;
+        if (w0) { rec[p] = (u8)l; rec[p + 1] = (u8)(l >> 8); }
+        copy_bytes(rec + p + 2, d.ids, l, tid, nthr);
+        p += 2 + l;
+    } else {
+        copy_bytes(rec + p, obuf + d.obase[ST_NAME], s.olen[ST_NAME], tid, nthr);
+        p += s.olen[ST_NAME];
+    }
+    // Qual (tag 7)
+    u32 qmd5 = (cfg.md5 && !cfg.lossy) ? 16 : 0;
+    if (w0) { put_tag(rec + p, 7); put_size4(rec + p + 1, qmd5 + s.olen[ST_QUAL]); }
+    p += 5;
+    if (qmd5) { copy_bytes(rec + p, s.md5[2], 16, tid, nthr); p += 16; }
+    copy_bytes(rec + p, obuf + d.obase[ST_QUAL], s.olen[ST_QUAL], tid, nthr);
+    p += s.olen[ST_QUAL];
+    // Dege streams (tags 23, 14, 24, 25, 26): u32le count + range-coder bytes, omitted when empty
+    {
+        u64 o = 6ull * d.nreads + 16;                              // region offsets as laid out by k_side
+        u32 nch = (u32)d.seqbytes - s.acgt, nf = s.side_cnt[3];
+        u64 offs[6] = {0, o, o + 2ull * d.nreads + 16, 0, 0, 0};
+        offs[3] = offs[2] + 2ull * nch + 16;
+        offs[4] = offs[3] + 2ull * nf + 16;
+        offs[5] = offs[4] + 8ull * nf + 16;
+        for (int k = 1; k < 6; k++) {
+            if (!s.side_cnt[k]) continue;
+            if (w0) { put_tag(rec + p, c_side_tag[k]); put_size4(rec + p + 1, 4 + s.side_len[k]); put_u32le(rec + p + 5, s.side_cnt[k]); }
+            p += 9;
+            copy_bytes(rec + p, sidebuf + d.sidebase + offs[k], s.side_len[k], tid, nthr);
+            p += s.side_len[k];
+        }
+    }
+    // Seq (tag 6)
+    if (w0) { put_tag(rec + p, 6); put_size4(rec + p + 1, (cfg.md5 ? 16 : 0) + s.olen[ST_SEQ]); }
+    p += 5;
+    if (cfg.md5) { copy_bytes(rec + p, s.md5[1], 16, tid, nthr); p += 16; }
+    copy_bytes(rec + p, obuf + d.obase[ST_SEQ], s.olen[ST_SEQ], tid, nthr);
+}
+
+// =============================================================================================
+// host-side launchers (called from sq_api.cu)
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+
+cudaError_t sqk_prep(const EncWave &w, cudaStream_t st, u64 *launches) {
+    if (w.R == 0) return cudaSuccess;
+    k_read_prep<<<cdiv(w.R, 256), 256, 0, st>>>(w.bd, w.bs, w.rbase, w.B, w.R, w.seqoff, w.idoff);
+    ScanArgs a{};
+    a.arr[0] = w.seqoff; a.arr[1] = w.idoff;
+    k_excl_scan<<<dim3(w.B, 2), 1024, 0, st>>>(a, w.rbase, w.totals + 3 * w.B, w.B);
+    k_check_totals<<<cdiv(w.B, 128), 128, 0, st>>>(w.bd, w.bs, w.totals + 3 * w.B, w.totals + 4 * w.B, w.B);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_rblock(const EncWave &w, double r, cudaStream_t st, u64 *launches) {
+    k_rblock<<<cdiv(w.B, 32), 32, 0, st>>>(w.bd, w.B, r);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_count(const EncWave &w, cudaStream_t st, u64 *launches) {
+    if (w.R == 0) {
+        k_set_counts<<<cdiv(w.B, 128), 128, 0, st>>>(w.bs, w.totals, w.B, !w.id_rule);
+        *launches += 1;
+        return cudaGetLastError();
+    }
+    u32 gw = cdiv((u64)w.R * 32, 256);
+    k_seq_pass<false><<<gw, 256, 0, st>>>(w.bd, w.bs, w.rbase, w.B, w.R, w.seqoff, w.acgtoff, w.tip, nullptr, w.seqmask);
+    k_qual_pass<false><<<gw, 256, 0, st>>>(w.bd, w.bs, w.rbase, w.B, w.R, w.seqoff, w.qlen2, w.qoff, nullptr, w.qlevel);
+    if (!w.id_rule)
+        k_name_pass<false><<<cdiv(w.R, 128), 128, 0, st>>>(w.bd, w.bs, w.rbase, w.B, w.R, w.idoff, w.np, w.ns, w.noff, nullptr);
+    ScanArgs a{};
+    a.arr[0] = w.acgtoff; a.arr[1] = w.qoff; a.arr[2] = w.noff;
+    k_excl_scan<<<dim3(w.B, w.id_rule ? 2 : 3), 1024, 0, st>>>(a, w.rbase, w.totals, w.B);
+    k_set_counts<<<cdiv(w.B, 128), 128, 0, st>>>(w.bs, w.totals, w.B, !w.id_rule);
+    *launches += w.id_rule ? 4 : 5;
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_emit(const EncWave &w, int stream, u64 *elem, cudaStream_t st, u64 *launches) {
+    if (w.R == 0) return cudaSuccess;
+    u32 gw = cdiv((u64)w.R * 32, 256);
+    if (stream == ST_SEQ)
+        k_seq_pass<true><<<gw, 256, 0, st>>>(w.bd, w.bs, w.rbase, w.B, w.R, w.seqoff, w.acgtoff, w.tip, elem, w.seqmask);
+    else if (stream == ST_QUAL)
+        k_qual_pass<true><<<gw, 256, 0, st>>>(w.bd, w.bs, w.rbase, w.B, w.R, w.seqoff, w.qlen2, w.qoff, elem, w.qlevel);
+    else
+        k_name_pass<true><<<cdiv(w.R, 128), 128, 0, st>>>(w.bd, w.bs, w.rbase, w.B, w.R, w.idoff, w.np, w.ns, w.noff, elem);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+template <int BITS>
+static cudaError_t sort_pass(const EncWave &w, int stream, const u64 *src, u64 *dst, int shift, u32 maxtiles,
+                             cudaStream_t st, u64 *launches) {
+    constexpr int D = 1 << BITS;
+    const int WPC = SQ_SORT_THREADS / 32;
+    size_t smem = (size_t)WPC * D * sizeof(u32);
+    dim3 grid(cdiv(maxtiles, WPC), w.B);
+    k_sort_hist<BITS><<<grid, SQ_SORT_THREADS, smem, st>>>(src, w.hist, w.bd, w.bs, stream, shift, maxtiles);
+    k_sort_scan<<<w.B, 1024, 0, st>>>(w.hist, (u64)D * maxtiles);
+    k_sort_scatter<BITS><<<grid, SQ_SORT_THREADS, smem, st>>>(src, dst, w.hist, w.bd, w.bs, stream, shift, maxtiles);
+    *launches += 3;
+    return cudaGetLastError();
+}
+
+// sorts elemA (in place result pointer returned): keybits context bits, digits of SQ_SORT_BITS
+cudaError_t sqk_sort(const EncWave &w, int stream, int keybits, u64 *a, u64 *b, u64 **sorted, cudaStream_t st, u64 *launches) {
+    u32 maxtiles = cdiv(w.maxbound[stream], SQ_TILE);
+    u64 *src = a, *dst = b;
+    if (maxtiles == 0) { *sorted = a; return cudaSuccess; }
+    for (int shift = 0; shift < keybits; shift += SQ_SORT_BITS) {
+        CK(sort_pass<SQ_SORT_BITS>(w, stream, src, dst, shift, maxtiles, st, launches));
+        u64 *t = src; src = dst; dst = t;
+    }
+    *sorted = src;
+    return cudaSuccess;
+}
+
+cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *triples, cudaStream_t st, u64 *launches) {
+    if (w.maxbound[stream] == 0) return cudaSuccess;
+    CK(cudaMemsetAsync(w.nseg, 0, 4 * sizeof(u32), st));
+    dim3 g(cdiv(w.maxbound[stream], 256), w.B);
+    k_seglist<<<g, 256, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.segcap);
+    *launches += 1;
+    int nsm = w.nsm;
+    if (stream == ST_SEQ) {
+        k_replay_seq<<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, triples, w.snap_seq);
+        *launches += 1;
+    } else if (stream == ST_QUAL) {
+        const int BD = 128;
+        size_t smem = (size_t)95 * BD * 4;
+        k_replay_sm<95, BD><<<nsm * 4, BD, smem, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1, triples,
+                                                     0, 1u << 24, w.snap_qual, 293);
+        *launches += 1;
+    } else {
+        const int BD1 = 64, BD2 = 128;
+        k_replay_sm<256, BD1><<<nsm * 3, BD1, (size_t)256 * BD1 * 4, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1,
+                                                                         triples, 0, NK_MIDDLE, w.snap_name, 776);
+        k_replay_sm<128, BD2><<<nsm * 3, BD2, (size_t)128 * BD2 * 4, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 2,
+                                                                         triples, NK_MIDDLE, NK_TOTAL,
+                                                                         w.snap_name ? w.snap_name + 3ull * 256 * 776 : nullptr, 392);
+        *launches += 2;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_rc(const EncWave &w, cudaStream_t st, u64 *launches) {
+    k_rc<<<dim3(w.B, 3), 32, 0, st>>>(w.bd, w.bs, w.triples[ST_SEQ], w.triples[ST_QUAL], w.triples[ST_NAME], w.obuf, w.id_rule);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_md5(const EncWave &w, cudaStream_t st, u64 *launches) {
+    k_md5<<<cdiv(3ull * w.B, 32), 32, 0, st>>>(w.bd, w.bs, w.B);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_side(const EncWave &w, cudaStream_t st, u64 *launches) {
+    k_side<<<w.B, 160, 0, st>>>(w.bd, w.bs, w.rbase, w.seqoff, w.tip, w.sidebuf);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launches) {
+    PackCfg cfg{w.md5, w.lossy, w.id_rule};
+    k_layout<<<1, 1024, 0, st>>>(w.bd, w.bs, w.B, cfg, w.recbuf, w.recbuf_cap, w.recoff, compact);
+    k_pack<<<dim3(32, w.B), 256, 0, st>>>(w.bd, w.bs, cfg, w.obuf, w.sidebuf);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_enc_attrs() {
+    CK(cudaFuncSetAttribute(k_replay_sm<95, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 95 * 128 * 4));
+    CK(cudaFuncSetAttribute(k_replay_sm<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 64 * 4));
+    CK(cudaFuncSetAttribute(k_replay_sm<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
+    CK(cudaFuncSetAttribute(k_sort_hist<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
+    CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
+    return cudaSuccess;
+}

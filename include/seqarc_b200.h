@@ -1,0 +1,138 @@
+/*
+ * seqarc_b200.h -- C ABI of the B200-native SeqArc v1.6 entropy-coding path.
+ *
+ * The reference (BGI-flexlab/fastqueeze, shipped as the unstripped binary
+ * /root/reference/SeqArc-1.6) has no plugin/FFI boundary.  The seam this
+ * library replaces is the per-worker coder object:
+ *
+ *   int EncapFqzComp::doFqzEncode(SeqArcMemBuf*, DebugInfo*)   @0x42d2d0  (called from doTask @0x433e9a)
+ *   int EncapFqzComp::doDecode  (SeqArcMemBuf*, DebugInfo*)    @0x42eb60  (called from decodeData)
+ *
+ * One sq_ctx stands where one EncapFqzComp (+ its SeqArcMemBuf) stands, except that it takes a
+ * BATCH of independent blocks (every model resets per block) and runs them on one
+ * GPU.  Plain pointers and sizes only; no torch / CUDA types in any signature.
+ *
+ * All functions return SQ_OK (0) or a negative sq_status; nothing aborts (the reference abort()s
+ * on a coder invariant @0x4220b8 and exit(1)s elsewhere).  There is NO CPU fallback: without a
+ * usable CUDA device sq_create fails with SQ_ERR_NO_DEVICE.
+ */
+#ifndef SEQARC_B200_H
+#define SEQARC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SQ_OK = 0,
+    SQ_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path never falls back to the CPU */
+    SQ_ERR_CUDA = -2,        /* a CUDA call failed; sq_last_error() has the text */
+    SQ_ERR_ARG = -3,         /* bad argument (null pointer, n <= 0, unsupported option) */
+    SQ_ERR_CAPACITY = -4,    /* an output buffer is too small */
+    SQ_ERR_INPUT = -5,       /* input the reference coder cannot represent (ID > 255 B, quality > '~', ...) */
+    SQ_ERR_FORMAT = -6,      /* malformed block record on decode */
+    SQ_ERR_NOMEM = -7,
+    SQ_ERR_MD5_NAME = -8,    /* blockMd5Verify @0x414e00: "Name md5 unequal" */
+    SQ_ERR_MD5_SEQ = -9,
+    SQ_ERR_MD5_QUAL = -10
+} sq_status;
+
+/* The SeqArcParam fields the hot path reads ("Config / flags"). */
+typedef struct {
+    int32_t device;        /* CUDA ordinal this context is bound to */
+    int32_t usemodel;      /* SeqArcParam+0x8: start every block from the snapshot given to sq_load_model */
+    int32_t lossy;         /* SeqArcParam+0x1870 (-l) */
+    double  lossy_r;       /* SeqArcParam+0x1878 */
+    int32_t md5;           /* SeqArcParam+0x1880: embed / skip the 16-byte per-stream MD5s (hidden -n) */
+    int32_t slevel;        /* SeqArcParam+0x1b54, default 3 -> order-10 base context */
+    int32_t qlevel;        /* SeqArcParam+0x1b58, default 2 */
+    int32_t id_rule;       /* SeqArcParam+0x18a4 idbin[0]: 1 = rule-based ID path (first ID only) */
+    uint64_t workspace_bytes;  /* device workspace budget; 0 = 80 % of free device memory */
+    void   *stream;        /* cudaStream_t to launch on, or NULL for a private stream */
+} sq_params;
+
+/* One block as SeqArcMemBuf holds it at the doFqzEncode seam: concatenated buffers
+ * without separators, PE interleaved R1,R2,R1,R2 (getBlockReadPE @0x412920). */
+typedef struct {
+    uint32_t nreads;          /* membuf+0x4  */
+    int32_t  longflag;        /* membuf+0x2  (reads > 65535 bp; not supported: SQ_ERR_ARG) */
+    const uint8_t  *ids;      /* membuf+0x80: IDs without '@' */
+    const uint8_t  *seq;      /* membuf+0x88 */
+    const uint8_t  *qual;     /* membuf+0x90 */
+    const uint16_t *idlen;    /* membuf+0xc0 */
+    const int32_t  *seqlen;   /* membuf+0xd0 */
+    uint64_t idbytes, seqbytes;
+} sq_block_in;
+
+/* Encoded block record "tag 1 | size(4) | streams" (SURVEY App. A), as written at membuf+0x70. */
+typedef struct {
+    uint8_t *data;            /* caller buffer (host for sq_encode_blocks, device for *_dev) */
+    uint64_t cap;
+    uint64_t len;             /* out: bytes of the record (= return value of doFqzEncode) */
+    int32_t  status;          /* out: per-block sq_status */
+} sq_block_out;
+
+/* Decoded block: caller-provided buffers with capacities; the decoder fills counts and lengths. */
+typedef struct {
+    uint8_t  *ids;   uint64_t idcap;
+    uint8_t  *seq;   uint8_t *qual;  uint64_t seqcap;
+    uint16_t *idlen; int32_t *seqlen; uint32_t readcap;
+    uint32_t nreads;          /* out */
+    uint64_t idbytes, seqbytes;   /* out */
+    int32_t  status;          /* out */
+} sq_block_dec;
+
+typedef struct sq_ctx sq_ctx;
+
+/* EncapFqzComp::EncapFqzComp @0x42f2a0 + initModel @0x42ed00: bind to a device, size the workspace. */
+int  sq_create(const sq_params *p, sq_ctx **out);
+/* EncapFqzComp::~EncapFqzComp */
+void sq_destroy(sq_ctx *c);
+/* text of the last error on this context (or of the last failed sq_create when c == NULL) */
+const char *sq_last_error(const sq_ctx *c);
+
+/* EncapFqzComp::ReadModelFormMem @0x420fc0: install the model snapshot (trailer tag 6 payload
+ * after its "tag 1, u16 = 1" header; SaveModelToMem layout @0x420c00) used when usemodel = 1. */
+int  sq_load_model(sq_ctx *c, const uint8_t *blob, uint64_t len);
+/* bytes such a snapshot must have for this context's slevel / qlevel / id_rule */
+uint64_t sq_model_size(const sq_ctx *c);
+
+/* doFqzEncode @0x42d2d0 over a batch: HOST buffers in, HOST records out, order preserved.
+ * Copies host->device, runs the kernels, copies the records device->host. */
+int  sq_encode_blocks(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out);
+/* same with every pointer inside blocks[] / out[] being a DEVICE pointer on this context's GPU
+ * (16-byte aligned); no host<->device payload copies are made. */
+int  sq_encode_blocks_dev(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out);
+
+/* doDecode @0x42eb60 over a batch of block records (each starting at its tag-1 byte). */
+int  sq_decode_blocks(sq_ctx *c, const uint8_t *const *recs, const uint64_t *reclens, int n,
+                      sq_block_dec *out);
+int  sq_decode_blocks_dev(sq_ctx *c, const uint8_t *const *recs, const uint64_t *reclens, int n,
+                          sq_block_dec *out);
+
+/* EncapFqzComp::rblock @0x426c10 on its own (R-Block smoothing of one block's concatenated
+ * quality bytes, in place, HOST buffer). */
+int  sq_rblock(sq_ctx *c, uint8_t *qual, uint64_t n, double r);
+
+/* Measurement hooks (DebugInfo @0x420080 stands here in the reference): device time of the
+ * kernels of the last encode / decode call, per stage, in milliseconds (CUDA events on the
+ * context's stream).  names[i] are static strings; returns the number of stages filled. */
+int  sq_last_timings(const sq_ctx *c, const char **names, float *ms, int cap);
+/* number of kernel launches issued by the last encode / decode call */
+uint64_t sq_last_launches(const sq_ctx *c);
+/* how many blocks one wave of the last call held (workspace-limited) */
+int  sq_last_wave_blocks(const sq_ctx *c);
+
+/* Test hook: copy an intermediate device buffer of the LAST encoded wave to the host.
+ * what: 0 = seq triples (u64 cum|freq<<16|tot<<32 per coded base, stream order), 1 = qual triples,
+ * 2 = name triples, 3 = number of coded symbols per stream (3 x u64). block = index in the wave. */
+int  sq_debug_fetch(sq_ctx *c, int what, int block, void *dst, uint64_t cap, uint64_t *got);
+
+const char *sq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

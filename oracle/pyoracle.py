@@ -81,6 +81,8 @@ def lib():
             f = getattr(L, n)
             f.restype = C.c_int64
             f.argtypes = [C.c_void_p, C.POINTER(CBlock), C.c_void_p]
+        L.sqo_trace_stream.restype = C.c_int64
+        L.sqo_trace_stream.argtypes = [C.c_void_p, C.POINTER(CBlock), C.c_int, C.c_void_p, C.c_void_p]
         L.sqo_md5.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.sqo_rblock.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
         L.sqo_model_size.restype = C.c_uint64
@@ -127,6 +129,16 @@ class Oracle:
         cb = Block(blk.ids, blk.idlen, blk.seq, q, blk.seqlen).cblock()
         n = getattr(lib(), "sqo_stream_" + which)(self.h, C.byref(cb), out.ctypes.data)
         return out[:n].tobytes()
+
+    def trace(self, which, blk: Block) -> np.ndarray:
+        """Coding triples (cum | freq<<16 | tot<<32) of stream 0 seq / 1 qual / 2 name, in stream order."""
+        nmax = int(blk.ids.shape[0] + blk.seq.shape[0] + 4 * blk.nreads + 16)
+        tr = np.empty(nmax, dtype=np.uint64)
+        scratch = np.empty(2 * nmax + 64, dtype=np.uint8)
+        q = blk.qual.copy()
+        cb = Block(blk.ids, blk.idlen, blk.seq, q, blk.seqlen).cblock()
+        n = lib().sqo_trace_stream(self.h, C.byref(cb), which, tr.ctypes.data, scratch.ctypes.data)
+        return tr[:n].copy()
 
     def decode_block(self, rec: bytes, idcap=None, seqcap=None, readcap=None) -> Block:
         rec_a = np.frombuffer(rec, dtype=np.uint8)

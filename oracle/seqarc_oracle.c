@@ -50,7 +50,11 @@ static void rc_start_enc(RC *rc, uint8_t *out) { rc->low = 0; rc->range = 0xffff
 static void rc_finish_enc(RC *rc) {
     for (int i = 0; i < 8; i++) { *rc->out++ = (uint8_t)(rc->low >> 56); rc->low <<= 8; }
 }
+/* test hook: when set, every coded (cum, freq, tot) is appended as cum | freq<<16 | tot<<32 */
+static uint64_t *g_trace;
+static uint64_t g_ntrace;
 static void rc_encode(RC *rc, uint32_t cum, uint32_t freq, uint32_t tot) {
+    if (g_trace) g_trace[g_ntrace++] = (uint64_t)cum | ((uint64_t)freq << 16) | ((uint64_t)tot << 32);
     rc->range /= tot;
     rc->low += (uint32_t)(cum * rc->range);
     rc->range *= freq;
@@ -638,6 +642,16 @@ uint64_t sqo_save_model(sqo_ctx *c, uint8_t *out) {
     memcpy(s, c->seqtab, (size_t)c->nseq * 4); s += (size_t)c->nseq * 4;
     for (uint32_t i = 0; i < c->nqual; i++) s = sm_pack(c->qual + (size_t)i * SM_STRIDE(95), 95, s);
     return (uint64_t)(s - out);
+}
+
+/* test hook: the coding triples of one stream (0 seq, 1 qual, 2 name) in stream order */
+int64_t sqo_trace_stream(sqo_ctx *c, const sqo_block *b, int which, uint64_t *triples, uint8_t *scratch) {
+    g_trace = triples; g_ntrace = 0;
+    if (which == 0) sqo_stream_seq(c, b, scratch);
+    else if (which == 1) sqo_stream_qual(c, b, scratch);
+    else sqo_stream_name(c, b, scratch);
+    g_trace = NULL;
+    return (int64_t)g_ntrace;
 }
 
 #include "seqarc_oracle_dec.inc"

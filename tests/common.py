@@ -1,0 +1,77 @@
+"""Shared helpers of the test-suite: golden cases -> blocks + reference records."""
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import arcwalk, pyoracle as po  # noqa: E402
+from tools import synth_fastq as sf  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+MANIFEST = json.load(open(os.path.join(GOLD, "manifest.json")))
+CASES = sorted(MANIFEST)
+
+
+def case_fastq(name):
+    m = MANIFEST[name]
+    if m["src"] == "err":
+        return tuple(gzip.open(os.path.join(GOLD, "err_pe1000_%d.fq.gz" % k), "rb").read() for k in (1, 2))
+    blk = sf.make_block(**m["src"])
+    t = sf.to_fastq(blk)
+    return t if m["pe"] else (t,)
+
+
+def case_params(name):
+    """Coder options of a golden case as kwargs of pyoracle.Oracle / fastqueeze_b200.SeqArcParam."""
+    m = MANIFEST[name]
+    arc = arcwalk.parse_arc(open(os.path.join(GOLD, name + ".arc"), "rb").read())
+    cfg = m["config"] or {}
+    idbin = arc["trailer"]["params"][15]
+    kw = dict(usemodel=0, lossy=0, lossy_r=0.0, md5=0 if "-n" in m["opts"] else 1,
+              slevel=int(cfg.get("Slevel", 3)), qlevel=int(cfg.get("Qlevel", 2)), id_rule=int(idbin[0]))
+    if "-l" in m["opts"]:
+        kw["lossy"] = 1
+        kw["lossy_r"] = float(m["opts"][m["opts"].index("-l") + 1])
+    return kw, arc
+
+
+def case_blocks(name):
+    """[(pyoracle.Block, reference record bytes)] for every block of the golden archive."""
+    m = MANIFEST[name]
+    kw, arc = case_params(name)
+    fq = case_fastq(name)
+    idx = arcwalk.block_index(arc, m["pe"])
+    out = []
+    nb = len(arc["blocks"])
+    for i, b in enumerate(arc["blocks"]):
+        if nb == 1:
+            parts = fq
+        else:   # cut the source text at the offsets the reference recorded in its block index
+            assert not m["pe"]
+            s = idx[i]["offs"][1]
+            e = idx[i + 1]["offs"][1] if i + 1 < nb else len(fq[0])
+            parts = (fq[0][s:e],)
+        blk = po.block_from_fastq(*parts)
+        out.append((blk, b["raw"]))
+    return kw, out
+
+
+def to_membuf(blk):
+    from fastqueeze_b200 import SeqArcMemBuf
+    return SeqArcMemBuf(blk.ids, blk.idlen, blk.seq, blk.qual, blk.seqlen)
+
+
+def to_param(kw, model=None):
+    from fastqueeze_b200 import SeqArcParam
+    return SeqArcParam(usemodel=kw["usemodel"], lossy=kw["lossy"], lossy_r=kw["lossy_r"], md5=kw["md5"],
+                       Slevel=kw["slevel"], Qlevel=kw["qlevel"], id_rule=kw["id_rule"], modelbuf=model)
+
+
+def synth_block(**kw):
+    d = sf.make_block(**kw)
+    return po.Block(d["ids"], d["idlen"], d["seq"], d["qual"], d["seqlen"])

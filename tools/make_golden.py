@@ -1,0 +1,97 @@
+"""TEST INFRASTRUCTURE -- regenerate tests/golden/ by running the UNMODIFIED reference binary.
+
+Run in the build container (needs oracle/_ref/SeqArc-1.6, staged by `make -C oracle ref` from
+/root/reference).  Every case writes   tests/golden/<name>.arc   (what `SeqArc-1.6 -c -t 1` wrote)
+and an entry in tests/golden/manifest.json (how the input is rebuilt, md5 of the FASTQ text,
+options).  Inputs are either the committed tests/golden/err_pe1000_{1,2}.fq.gz (first 1000 pairs
+of the reference's own test/ERR2755197_test_{1,2}.fq) or seeded synthetic blocks
+(tools/synth_fastq.py), so nothing under /root/reference is needed at test time.
+"""
+import gzip
+import hashlib
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+from tools import synth_fastq as sf  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+CASES = [
+    # name, input spec, reference options, seqarc.config
+    dict(name="err_pe1000", src="err", pe=True, opts=[], config=None),
+    dict(name="err_pe1000_nomd5", src="err", pe=True, opts=["-n"], config=None),
+    dict(name="illumina_pe150", src=dict(kind="illumina_pe150", n_templates=1500, seed=7), pe=True, opts=[], config=None),
+    dict(name="illumina_pe150_n", src=dict(kind="illumina_pe150", n_templates=1500, seed=11, n_rate=0.004, hash_tail=0.05),
+         pe=True, opts=[], config=None),
+    dict(name="illumina_pe150_lossy", src=dict(kind="illumina_pe150", n_templates=1500, seed=7), pe=True,
+         opts=["-l", "1.15"], config=None, shim=True),
+    dict(name="se100_q8", src=dict(kind="se100_q8", n_templates=4000, seed=12345), pe=False, opts=[], config=None),
+    dict(name="se100_q8_3blocks", src=dict(kind="se100_q8", n_templates=12000, seed=5), pe=False, opts=[],
+         config={"BlockSize(M)": 1}),
+    dict(name="srr_pe100", src=dict(kind="srr_pe100", n_templates=1200, seed=3), pe=True, opts=[], config=None),
+    dict(name="illumina_pe150_q1", src=dict(kind="illumina_pe150", n_templates=800, seed=21, hash_tail=0.1), pe=True, opts=[],
+         config={"Qlevel": 1}),
+    dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
+         config={"Qlevel": 3, "Slevel": 2}),
+]
+
+
+def case_fastq(case):
+    """FASTQ text of a case: (r1, r2) for PE, (r1,) for SE."""
+    if case["src"] == "err":
+        return tuple(gzip.open(os.path.join(GOLD, "err_pe1000_%d.fq.gz" % k), "rb").read() for k in (1, 2))
+    blk = sf.make_block(**case["src"])
+    t = sf.to_fastq(blk)
+    return t if case["pe"] else (t,)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    assert po.have_ref(), "reference binary not staged (make -C oracle ref)"
+    # committed real-data subset: first 1000 pairs of the reference's own test files
+    for k in (1, 2):
+        dst = os.path.join(GOLD, "err_pe1000_%d.fq.gz" % k)
+        if not os.path.exists(dst):
+            src = "/root/reference/test/ERR2755197_test_%d.fq" % k
+            lines = open(src, "rb").read().split(b"\n")[:4000]
+            with open(dst, "wb") as f:
+                with gzip.GzipFile(fileobj=f, mode="wb", mtime=0) as g:
+                    g.write(b"\n".join(lines) + b"\n")
+    manifest = {}
+    for case in CASES:
+        fq = case_fastq(case)
+        tmp = tempfile.mkdtemp(prefix="gold_")
+        try:
+            names = []
+            for k, t in enumerate(fq):
+                p = os.path.join(tmp, "in_%d.fq" % (k + 1))
+                open(p, "wb").write(t)
+                names.append(p)
+            args = ["-c", "-t", "1", "-f"] + case["opts"]
+            if case["pe"]:
+                args += ["-1", names[0], "-2", names[1]]
+            else:
+                args += ["-1", names[0]]
+            args += ["-o", "out"]
+            rc, log = po.run_ref(args, tmp, lossy_shim=case.get("shim", False), config=case["config"])
+            assert rc == 0, (case["name"], rc, log[-2000:])
+            arc = open(os.path.join(tmp, "out.arc"), "rb").read()
+            open(os.path.join(GOLD, case["name"] + ".arc"), "wb").write(arc)
+            manifest[case["name"]] = dict(src=case["src"], pe=case["pe"], opts=case["opts"], config=case["config"],
+                                          shim=case.get("shim", False), arc_bytes=len(arc),
+                                          arc_md5=hashlib.md5(arc).hexdigest(),
+                                          fastq_md5=[hashlib.md5(t).hexdigest() for t in fq])
+            print(case["name"], len(arc), "bytes")
+        finally:
+            shutil.rmtree(tmp)
+    json.dump(manifest, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
