@@ -86,13 +86,14 @@ __global__ void __launch_bounds__(32) k_dec_len(DecBlock *db) {
 
 // ---------------------------------------------------------------------------------------------
 // decode_name @0x428380
-SQ_D int decode_name(DecBlock &d, RcDec &rc, u8 *name, u8 *last, int &lnl, int &lpl, int &lsl) {
+SQ_D int decode_name(DecBlock &d, RcDec &rc, u8 *name, u64 room, u8 *last, int &lnl, int &lpl, int &lsl) {
     M256 *prefix = (M256 *)d.nametab, *suffix = prefix + 256, *lenm = suffix + 256;
     M128 *middle = (M128 *)(lenm + 256);
     int p = (int)prefix[lpl].decode(rc);
     int s = (int)suffix[lsl].decode(rc);
     int n = (int)lenm[lnl].decode(rc);
     lpl = p; lsl = s;
+    if ((u64)n > room) return -1;                                          // caller's ID buffer is full
     if (p > n || s > n - p || s > lnl) { p = p > n ? n : p; s = 0; }       // corrupt stream guard
     for (int i = 0; i < p; i++) name[i] = last[i];
     int len2 = n - s, lc2 = (p != 0), i = p, j = p, k = 0;
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int qlevel, int i
         rc.start(d.rec + d.off[5], d.rec + d.off[5] + d.len[5]);
         u64 o = 0;
         for (u32 r = 0; r < d.nreads; r++) {
-            if (o + 256 > d.idcap) { d.status = SQ_ERR_CAPACITY_K; return; }
-            int n = decode_name(d, rc, d.ids + o, sm.last_name, lnl, lpl, lsl);
+            int n = decode_name(d, rc, d.ids + o, d.idcap - o, sm.last_name, lnl, lpl, lsl);
+            if (n < 0) { d.status = SQ_ERR_CAPACITY_K; return; }
             d.idlen[r] = (u16)n;
             o += (u32)n;
         }
