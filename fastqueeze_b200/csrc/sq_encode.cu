@@ -5,8 +5,9 @@
 // block's encode is decomposed into
 //   1. context kernels      : (context key, symbol, stream position) per coded symbol, coalesced
 //   2. stable radix sort    : group symbols by context inside each block, stream order kept
-//   3. model replay         : one thread per non-empty context replays that context's adaptive
-//                             model over its own symbols and emits (cum, freq, tot) per symbol
+//   3. model replay         : one thread (bases) or one warp (SIMPLE_MODEL) per non-empty context
+//                             replays that context's adaptive model over its own symbols and emits
+//                             (cum, freq, tot) per symbol
 //   4. range-coder pass     : the only serial part -- one warp per (block, stream) runs the
 //                             64-bit low / 32-bit range recurrence over the triples
 //   5. pack                 : tags, sizes, MD5s and side streams are laid out as the block record
@@ -405,6 +406,8 @@ SQ_D u32 grab32(u32 *cursor, int lane) {
 
 // 3b. base model replay (fqzcomp BASE_MODEL<uint8_t>, @0x421f7f-0x422087): 4 byte counters per
 // context, init 3 (or the snapshot's table), halve when the sum exceeds 253 BEFORE coding.
+// One thread per context; the element stream of a context is contiguous after the sort, so the
+// next element is fetched one step ahead and the line after next is prefetched into L1.
 __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockDesc *bd, const BlockState *bs,
                                                     const u64 *seglist, const u32 *nseg, u32 *cursor,
                                                     u64 *triples, const u8 *snap_seq) {
@@ -425,7 +428,10 @@ __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockD
         u32 S0 = 3, S1 = 3, S2 = 3, S3 = 3;
         if (snap_seq) { const u8 *t = snap_seq + (u64)key * 4; S0 = t[0]; S1 = t[1]; S2 = t[2]; S3 = t[3]; }
         u64 *out = triples + eb;
+        bool hn = g + 1 < end;
+        u64 en = hn ? src[g + 1] : 0;
         for (;;) {
+            if ((g & 15) == 0 && g + 32 < end) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + g + 32));
             u32 sym = el_sym(e);
             u32 tot = S0 + S1 + S2 + S3;
             if (tot > 253) {
@@ -438,129 +444,244 @@ __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockD
             else if (sym == 2) { cum = S0 + S1; f = S2; S2 = (S2 + 1) & 0xff; }
             else { cum = S0 + S1 + S2; f = S3; S3 = (S3 + 1) & 0xff; }
             out[el_pos(e)] = tr_make(cum, f, tot);
-            if (++g >= end) break;
-            e = src[g];
+            if (!hn) break;
+            e = en;
+            g++;
             if (el_key(e) != key) break;
+            hn = g + 1 < end;
+            if (hn) en = src[g + 1];
         }
     }
 }
 
-// 3c. SIMPLE_MODEL<N> replay (encodeSymbol @0x4221fb-0x4222f1).  The model of the thread's
-// context lives in shared memory, transposed (word w of thread t at w*BD + t) so that every lane
-// always hits its own bank.  keylo/keyhi select which contexts this launch handles; snap (may be
-// null) + snapstride give the packed snapshot model of key `keylo + k` at snap + k*snapstride.
-template <int N, int BD>
-__global__ void __launch_bounds__(BD) k_replay_sm(const u64 *src, const BlockDesc *bd, const BlockState *bs, int stream,
-                                                  const u64 *seglist, const u32 *nseg, u32 *cursor, u64 *triples,
-                                                  u32 keylo, u32 keyhi, const u8 *snap, u32 snapstride) {
-    extern __shared__ u32 smem[];
-    u32 *F = smem + threadIdx.x;                 // F[k] at F[k * BD]
+// 3c. SIMPLE_MODEL<N> replay (encodeSymbol @0x4221fb-0x4222f1), one WARP per context.
+// The model lives in registers, blocked over the lanes: lane l holds F[l*EPL .. l*EPL+EPL) as
+// (sym, freq) pairs, so finding the coded symbol is one ballot, its cumulative frequency one
+// warp reduction, and the +8 / halve / bubble-swap updates are lane-local (plus one neighbour
+// exchange when a swap crosses a lane boundary).  Elements are fetched 32 at a time, coalesced.
+// keylo/keyhi select the contexts this launch handles; snap (may be null) + snapstride give the
+// packed snapshot model of key keylo + k at snap + k * snapstride.
+template <int N, int EPL>
+__global__ void __launch_bounds__(128) k_replay_warp(const u64 *src, const BlockDesc *bd, const BlockState *bs, int stream,
+                                                     const u64 *seglist, const u32 *nseg, u32 *cursor, u64 *triples,
+                                                     u32 keylo, u32 keyhi, const u8 *snap, u32 snapstride) {
+    static_assert(EPL * 32 >= N, "lanes must cover the model");
     int lane = threadIdx.x & 31;
     u32 total = *nseg;
     for (;;) {
-        u32 base = grab32(cursor, lane);
-        if (base >= total) break;
-        u32 idx = base + lane;
-        if (idx >= total) continue;
+        u32 idx = 0;
+        if (lane == 0) idx = atomicAdd(cursor, 1u);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= total) break;
         u64 ent = seglist[idx];
         int b = (int)(ent >> 40);
         u64 g = ent & (((u64)1 << 40) - 1);
-        u64 e = src[g];
-        u32 key = el_key(e);
+        u32 key = el_key(src[g]);
         if (key < keylo || key >= keyhi) continue;
         u64 eb = bd[b].ebase[stream];
         u64 end = eb + bs[b].nsym[stream];
+        u64 *out = triples + eb;
+        u32 sy[EPL], fr[EPL];
         u32 tot, bub;
         if (snap) {
             const u8 *s = snap + (u64)(key - keylo) * snapstride;
             tot = get_u32le(s); bub = get_u32le(s + 4);
-            s += 8;
-            for (int k = 0; k < N; k++, s += 3) F[k * BD] = (u32)s[0] | ((u32)(s[1] | (s[2] << 8)) << 16);
+#pragma unroll
+            for (int i = 0; i < EPL; i++) {
+                int slot = lane * EPL + i;
+                const u8 *q = s + 8 + 3 * slot;
+                sy[i] = slot < N ? q[0] : 0xffffu;
+                fr[i] = slot < N ? (u32)(q[1] | (q[2] << 8)) : 0;
+            }
         } else {
             tot = N; bub = 0;
-            for (int k = 0; k < N; k++) F[k * BD] = (u32)k | (1u << 16);
+#pragma unroll
+            for (int i = 0; i < EPL; i++) {
+                int slot = lane * EPL + i;
+                sy[i] = slot < N ? (u32)slot : 0xffffu;
+                fr[i] = slot < N ? 1 : 0;
+            }
         }
-        u64 *out = triples + eb;
+        u64 gi = g + lane;
+        u64 e = gi < end ? src[gi] : ~(u64)0;
         for (;;) {
-            u32 sym = el_sym(e);
-            u32 cum = 0;
-            int k = 0;
-            u32 fk = F[0];
-            while ((fk & 0xffffu) != sym && k < N - 1) { cum += fk >> 16; k++; fk = F[k * BD]; }
-            u32 f = fk >> 16;
-            out[el_pos(e)] = tr_make(cum, f, tot);
-            f += 8; tot += 8;
-            fk = (fk & 0xffffu) | (f << 16);
-            F[k * BD] = fk;
-            if (tot > 0xffe0u) {
-                tot = 0;
-                for (int j = 0; j < N; j++) {
-                    u32 x = F[j * BD], gq = x >> 16;
-                    gq -= gq >> 1;
-                    F[j * BD] = (x & 0xffffu) | (gq << 16);
-                    tot += gq;
+            bool valid = gi < end && el_key(e) == key;
+            u32 vb = __ballot_sync(FULL, valid);
+            int cnt = (vb == FULL) ? 32 : (__ffs(~vb) - 1);
+            u64 gn = gi + 32;
+            u64 en = (cnt == 32 && gn < end) ? src[gn] : ~(u64)0;      // next group, in flight while this one is replayed
+            u32 mysym = el_sym(e);
+            u64 mytr = 0;
+            for (int j = 0; j < cnt; j++) {
+                u32 s = __shfl_sync(FULL, mysym, j);
+                int li = -1;
+#pragma unroll
+                for (int i = 0; i < EPL; i++) if (sy[i] == s) li = i;
+                u32 bal = __ballot_sync(FULL, li >= 0);
+                int kl = bal ? (__ffs(bal) - 1) : 31;
+                u32 T = 0, part = 0, fsel = 0;
+#pragma unroll
+                for (int i = 0; i < EPL; i++) {
+                    if (i < li) part += fr[i];
+                    if (i == li) fsel = fr[i];
+                    T += fr[i];
                 }
-                fk = F[k * BD];
+                u32 contrib = lane < kl ? T : (lane == kl ? part : 0);
+                u32 cum = __reduce_add_sync(FULL, contrib);
+                u32 freq = __shfl_sync(FULL, fsel, kl);
+                if (lane == j) mytr = tr_make(cum, freq, tot);
+                // update: Freq += 8, TotFreq += 8, halve when TotFreq > 0xffe0 (@0x4222b7)
+                if (lane == kl) {
+#pragma unroll
+                    for (int i = 0; i < EPL; i++) if (i == li) fr[i] += 8;
+                }
+                tot += 8;
+                if (tot > 0xffe0u) {
+                    u32 t2 = 0;
+#pragma unroll
+                    for (int i = 0; i < EPL; i++) { fr[i] -= fr[i] >> 1; t2 += fr[i]; }
+                    tot = __reduce_add_sync(FULL, t2);
+                }
+                // bubble swap with the predecessor every 16th symbol if strictly greater (@0x4222d3-0x4222f1)
+                if (((++bub) & 15) == 0) {
+                    u32 up_s = __shfl_up_sync(FULL, sy[EPL - 1], 1), up_f = __shfl_up_sync(FULL, fr[EPL - 1], 1);
+                    u32 cur_s = 0, cur_f = 0, prv_s = up_s, prv_f = up_f;
+#pragma unroll
+                    for (int i = 0; i < EPL; i++) {
+                        if (i == li) { cur_s = sy[i]; cur_f = fr[i]; }
+                        if (i + 1 == li) { prv_s = sy[i]; prv_f = fr[i]; }
+                    }
+                    bool dosw = (lane == kl) && (kl * EPL + li > 0) && cur_f > prv_f;
+                    u32 swb = __ballot_sync(FULL, dosw);
+                    if (swb) {                                   // uniform
+                        int lik = __shfl_sync(FULL, li, kl);
+                        u32 cs = __shfl_sync(FULL, cur_s, kl), cf = __shfl_sync(FULL, cur_f, kl);
+                        if (lik > 0) {
+                            if (lane == kl) {
+#pragma unroll
+                                for (int i = 1; i < EPL; i++) if (i == li) { sy[i] = prv_s; fr[i] = prv_f; sy[i - 1] = cur_s; fr[i - 1] = cur_f; }
+                            }
+                        } else {
+                            if (lane == kl) { sy[0] = prv_s; fr[0] = prv_f; }
+                            if (lane == kl - 1) { sy[EPL - 1] = cs; fr[EPL - 1] = cf; }
+                        }
+                    }
+                }
             }
-            if (((++bub) & 15) == 0 && k > 0) {
-                u32 pk = F[(k - 1) * BD];
-                if ((fk >> 16) > (pk >> 16)) { F[k * BD] = pk; F[(k - 1) * BD] = fk; }
-            }
-            if (++g >= end) break;
-            e = src[g];
-            if (el_key(e) != key) break;
+            if (lane < cnt) out[el_pos(e)] = mytr;
+            if (cnt < 32) break;
+            gi = gn;
+            e = en;
+            if (gi - lane >= end) break;
         }
     }
 }
 
 // =============================================================================================
-// 4. range-coder pass: one warp per (block, stream).  Lanes fetch 32 triples coalesced and turn
-// each `tot` into a multiply-shift divisor in parallel; lane 0 then runs the serial recurrence
-// (RangeCoder::Encode @0x422010-0x422085) over the 32 prepared records and emits bytes.
-__global__ void __launch_bounds__(32) k_rc(const BlockDesc *bd, BlockState *bs, const u64 *tr_seq, const u64 *tr_qual,
+// 4. range-coder pass (RangeCoder::Encode @0x422010-0x422085, flush @0x424a30): the only strictly
+// serial part of the encoder.  One CTA of two warps per (block, stream):
+//   warp 1 (producer) streams the triples in, 32 per step and coalesced, and turns each `tot`
+//          into the 64-bit multiplier M = ceil(2^64 / tot) (floor(r / tot) = hi64(r * M), exact for
+//          r < 2^32, tot <= 2^16), filling a small shared-memory ring;
+//   warp 0 lane 0 (consumer) runs the recurrence.  The common path is branch free: at most two
+//          renormalisation shifts per symbol, two bytes always stored, the cursor advanced by the
+//          shift count.  The carry-less range adjustment (@0x422040-0x422058) fires about once
+//          per 2^32 renormalisations; it is DETECTED on the fast path, and the 32-symbol group is
+//          then rolled back and re-run with the exact loop.
+#define RC_NBUF 4
+struct RcState { u64 low; u32 range; u32 nout; };
+
+SQ_D void rc_exact_step(RcState &s, u8 *out, u32 cum, u32 freq, u32 tot) {
+    s.range /= tot;
+    s.low += (u32)(cum * s.range);
+    s.range *= freq;
+    while (s.range < (1u << 24)) {
+        if ((s.low ^ (s.low + s.range)) >> 56) s.range = (((u32)s.low) | 0xffffffu) - (u32)s.low;
+        out[s.nout++] = (u8)(s.low >> 56);
+        s.range <<= 8;
+        s.low <<= 8;
+    }
+}
+
+// Fast step.  The coder's range is kept as (r0, sh): range = r0 << sh with sh in {0, 8, 16} the
+// pending renormalisation shift, so that the shift is folded into the next division:
+//   floor((r0 << sh) / tot) = bits [64 - sh, 96 - sh) of r0 * M   (r0 << sh < 2^32, no truncation)
+// and the serial dependency per symbol is IMAD.HI -> IMAD.WIDE -> funnel shift -> IMAD.
+// `evm` tracks min over the group of (~low >> 32) & 0xffff: it is 0 iff bits 32..47 of low were all
+// ones at some step, a NECESSARY condition for the carry-less adjustment (a carry out of the low 32
+// bits must ripple through them to change byte 7 or byte 6) -- a conservative rollback trigger.
+#define RC_FAST_STEP(rr)                                                                     \
+    {                                                                                        \
+        u32 t_ = __umulhi(r0, rr.x);                                                         \
+        u64 P_ = (u64)r0 * rr.y + t_;                                                        \
+        u32 q_ = __funnelshift_l((u32)P_, (u32)(P_ >> 32), sh);                              \
+        low += (u32)((rr.z & 0xffffu) * q_);                                                 \
+        r0 = q_ * rr.w;                                                                      \
+        evm = min(evm, ~(u32)(low >> 32) & 0xffffu);                                         \
+        op[0] = (u8)(low >> 56);                                                             \
+        op[1] = (u8)(low >> 48);                                                             \
+        u32 nb_ = (r0 < (1u << 24)) + (r0 < (1u << 16));                                     \
+        op += nb_;                                                                           \
+        sh = nb_ * 8;                                                                        \
+        low <<= sh;                                                                          \
+    }
+
+__global__ void __launch_bounds__(64) k_rc(const BlockDesc *bd, BlockState *bs, const u64 *tr_seq, const u64 *tr_qual,
                                            const u64 *tr_name, u8 *obuf, int skip_name) {
-    __shared__ uint4 rec[2][32];
-    int b = blockIdx.x, st = blockIdx.y, lane = threadIdx.x;
+    __shared__ uint4 rec[RC_NBUF][32];
+    __shared__ volatile u32 produced, consumed;
+    int b = blockIdx.x, st = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (st == ST_NAME && skip_name) return;
     const u64 *tr = (st == ST_SEQ ? tr_seq : st == ST_QUAL ? tr_qual : tr_name) + bd[b].ebase[st];
     u32 n = bs[b].nsym[st];
-    u8 *out = obuf + bd[b].obase[st];
-    u64 low = 0;
-    u32 range = 0xffffffffu;
-    u32 nout = 0;
-    u64 t = (lane < n) ? tr[lane] : 0;
-    int pp = 0;
-    for (u32 base = 0; base < n; base += 32, pp ^= 1) {
-        u32 cnt = min(32u, n - base);
-        if ((u32)lane < cnt) {
+    u32 ngroups = (n + 31) / 32;
+    if (threadIdx.x == 0) { produced = 0; consumed = 0; }
+    __syncthreads();
+    if (warp == 1) {
+        u64 t = (u32)lane < n ? tr[lane] : 0;
+        for (u32 g = 0; g < ngroups; g++) {
+            while (g >= consumed + RC_NBUF) __nanosleep(32);
             u32 tot = (u32)(t >> 32) & 0xffffu;
-            FastDiv fd = fastdiv_make(tot < 2 ? 2 : tot);
-            rec[pp][lane] = make_uint4(fd.m, fd.sh, (u32)t & 0xffffu, (u32)(t >> 16) & 0xffffu);
+            if (tot < 2) tot = 2;
+            u64 M = ~(u64)0 / tot + 1;
+            // x = M lo, y = M hi, z = cum | tot << 16, w = freq
+            rec[g % RC_NBUF][lane] = make_uint4((u32)M, (u32)(M >> 32), ((u32)t & 0xffffu) | (tot << 16), (u32)(t >> 16) & 0xffffu);
+            u64 nx = (u64)(g + 1) * 32 + lane;
+            t = nx < n ? tr[nx] : 0;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) produced = g + 1;
         }
-        u32 nx = base + 32 + lane;
-        t = (nx < n) ? tr[nx] : 0;                  // prefetch the next 32 while lane 0 codes
-        __syncwarp();
-        if (lane == 0) {
-            for (u32 j = 0; j < cnt; j++) {
-                uint4 rr = rec[pp][j];
-                u32 tt = __umulhi(rr.x, range);
-                u32 q = (tt + ((range - tt) >> 1)) >> rr.y;
-                low += (u32)(rr.z * q);
-                range = q * rr.w;
-                while (range < (1u << 24)) {
-                    if ((low ^ (low + range)) >> 56) range = (((u32)low) | 0xffffffu) - (u32)low;
-                    out[nout++] = (u8)(low >> 56);
-                    range <<= 8;
-                    low <<= 8;
-                }
-            }
+        return;
+    }
+    if (lane != 0) return;
+    u8 *out = obuf + bd[b].obase[st];
+    u8 *op = out;
+    u64 low = 0;
+    u32 r0 = 0xffffffffu, sh = 0;
+    for (u32 g = 0; g < ngroups; g++) {
+        while (produced <= g) { }
+        __threadfence_block();
+        const uint4 *rp = rec[g % RC_NBUF];
+        u32 cnt = min(32u, n - g * 32);
+        RcState save{low, r0 << sh, (u32)(op - out)};
+        u32 evm = 0xffffu;
+        if (cnt == 32) {
+#pragma unroll 8
+            for (int j = 0; j < 32; j++) { uint4 rr = rp[j]; RC_FAST_STEP(rr) }
+        } else {
+            for (u32 j = 0; j < cnt; j++) { uint4 rr = rp[j]; RC_FAST_STEP(rr) }
         }
-        __syncwarp();
+        if (evm == 0) {                 // a carry-less adjustment may have happened in this group: redo it exactly
+            RcState s = save;
+            for (u32 j = 0; j < cnt; j++) { uint4 rr = rp[j]; rc_exact_step(s, out, rr.z & 0xffffu, rr.w, rr.z >> 16); }
+            low = s.low; r0 = s.range; sh = 0; op = out + s.nout;
+        }
+        __threadfence_block();
+        consumed = g + 1;
     }
-    if (lane == 0) {
-        for (int i = 0; i < 8; i++) { out[nout++] = (u8)(low >> 56); low <<= 8; }
-        bs[b].olen[st] = nout;
-    }
+    for (int i = 0; i < 8; i++) { *op++ = (u8)(low >> 56); low <<= 8; }
+    bs[b].olen[st] = (u32)(op - out);
 }
 
 // =============================================================================================
@@ -967,25 +1088,22 @@ cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *tri
         k_replay_seq<<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, triples, w.snap_seq);
         *launches += 1;
     } else if (stream == ST_QUAL) {
-        const int BD = 128;
-        size_t smem = (size_t)95 * BD * 4;
-        k_replay_sm<95, BD><<<nsm * 4, BD, smem, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1, triples,
-                                                     0, 1u << 24, w.snap_qual, 293);
+        k_replay_warp<95, 3><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1, triples,
+                                                    0, 1u << 24, w.snap_qual, 293);
         *launches += 1;
     } else {
-        const int BD1 = 64, BD2 = 128;
-        k_replay_sm<256, BD1><<<nsm * 3, BD1, (size_t)256 * BD1 * 4, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1,
-                                                                         triples, 0, NK_MIDDLE, w.snap_name, 776);
-        k_replay_sm<128, BD2><<<nsm * 3, BD2, (size_t)128 * BD2 * 4, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 2,
-                                                                         triples, NK_MIDDLE, NK_TOTAL,
-                                                                         w.snap_name ? w.snap_name + 3ull * 256 * 776 : nullptr, 392);
+        k_replay_warp<256, 8><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1,
+                                                     triples, 0, NK_MIDDLE, w.snap_name, 776);
+        k_replay_warp<128, 4><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 2,
+                                                     triples, NK_MIDDLE, NK_TOTAL,
+                                                     w.snap_name ? w.snap_name + 3ull * 256 * 776 : nullptr, 392);
         *launches += 2;
     }
     return cudaGetLastError();
 }
 
 cudaError_t sqk_rc(const EncWave &w, cudaStream_t st, u64 *launches) {
-    k_rc<<<dim3(w.B, 3), 32, 0, st>>>(w.bd, w.bs, w.triples[ST_SEQ], w.triples[ST_QUAL], w.triples[ST_NAME], w.obuf, w.id_rule);
+    k_rc<<<dim3(w.B, 3), 64, 0, st>>>(w.bd, w.bs, w.triples[ST_SEQ], w.triples[ST_QUAL], w.triples[ST_NAME], w.obuf, w.id_rule);
     *launches += 1;
     return cudaGetLastError();
 }
@@ -1011,9 +1129,6 @@ cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launch
 }
 
 cudaError_t sqk_enc_attrs() {
-    CK(cudaFuncSetAttribute(k_replay_sm<95, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 95 * 128 * 4));
-    CK(cudaFuncSetAttribute(k_replay_sm<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 64 * 4));
-    CK(cudaFuncSetAttribute(k_replay_sm<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
     CK(cudaFuncSetAttribute(k_sort_hist<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
     CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
