@@ -12,6 +12,7 @@
 #include "sq_common.cuh"
 #include "sq_kernels.h"
 #include "sq_md5.cuh"
+#include <cstdio>
 
 #define FULL 0xffffffffu
 
@@ -20,22 +21,75 @@
 // the decoding warp, EPL consecutive entries per lane (lane l owns F[l*EPL .. l*EPL+EPL)):
 //   row i   (i < EPL), word l : entry i of lane l = sym | bub << 8 (row 0 only) | freq << 16
 //   row EPL,           word l : base_l | tot << 16, base_l = sum of the frequencies of all lower lanes
+//   row EPL+1,         word l : floor(2^32 / tot), so that range / tot is one multiply + one fix-up
 // Every word is only ever read and written by its own lane, every row is one coalesced 128-byte
 // access, and a symbol is found with EPL multiply-compares per lane + one ballot (no second division:
 // target = code / r  is replaced by comparing code with cum * r, which is the same test on integers).
 template <int N, int EPL> struct WM {
-    static constexpr int ROWS = EPL + 1;
+    static constexpr int ROWS = EPL + 2;
     static constexpr int STRIDE = ROWS * 32;          // words per model
 };
 #define WQ_STRIDE (WM<95, 3>::STRIDE)
 #define W256_STRIDE (WM<256, 8>::STRIDE)
 #define W128_STRIDE (WM<128, 4>::STRIDE)
+static_assert(WQ_STRIDE == SQ_WQ_STRIDE, "layout");
+static_assert(768ull * W256_STRIDE + 8192ull * W128_STRIDE == SQ_WNAME_WORDS, "layout");
 
 SQ_D u32 warp_incl_scan_d(u32 v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(FULL, v, o); if (lane >= o) v += t; }
     return v;
 }
+// floor(2^32 / tot), 2 <= tot <= 65535
+SQ_D u32 recip32(u32 tot) {
+    if ((tot & (tot - 1)) == 0) return 1u << (1 + __clz(tot));       // 2^32 / 2^k, k = 31 - clz
+    return 0xffffffffu / tot;
+}
+
+// Range decoder with a byte window: the next bytes of the stream sit in a register and are
+// refilled four at a time well before they are needed, so no load is on the symbol chain.
+struct RcDecW {
+    u64 low;
+    u32 range, code;
+    const u8 *in, *end;
+    u64 win;
+    int avail;
+    SQ_D void refill() {
+        u32 v;
+        if (in + 4 <= end) v = ((u32)in[0] << 24) | ((u32)in[1] << 16) | ((u32)in[2] << 8) | in[3];
+        else {
+            v = 0;
+            for (int k = 0; k < 4; k++) v = (v << 8) | (in + k < end ? in[k] : 0);
+        }
+        in += 4;
+        win |= (u64)v << (32 - 8 * avail);
+        avail += 4;
+    }
+    SQ_D u32 get() {
+        u32 b = (u32)(win >> 56);
+        win <<= 8;
+        avail--;
+        if (avail <= 4) refill();
+        return b;
+    }
+    SQ_D void start(const u8 *i, const u8 *e) {
+        low = 0; range = 0xffffffffu; code = 0; in = i; end = e; win = 0; avail = 0;
+        refill(); refill();
+        for (int k = 0; k < 8; k++) code = (code << 8) | get();
+    }
+    SQ_D void decode(u32 cum, u32 freq) {       // range already divided by tot
+        u32 t = cum * range;
+        low += t;
+        code -= t;
+        range *= freq;
+        while (range < (1u << 24)) {
+            if ((low ^ (low + range)) >> 56) range = (((u32)low) | 0xffffffu) - (u32)low;
+            code = (code << 8) | get();
+            range <<= 8;
+            low <<= 8;
+        }
+    }
+};
 
 // per-block model reset (compressQual @0x426f10-0x426f84 etc. reset every block) or snapshot
 // restore (unpack loops @0x42705c-0x42712e): one warp per model
@@ -64,6 +118,7 @@ __global__ void __launch_bounds__(256) k_init_wm(DecBlock *db, int which, u32 nm
 #pragma unroll
         for (int i = 0; i < EPL; i++) mp[i * 32 + lane] = w[i];
         mp[EPL * 32 + lane] = base | (tot << 16);
+        mp[(EPL + 1) * 32 + lane] = recip32(tot < 2 ? 2 : tot);
     }
 }
 __global__ void k_init_seqtab(DecBlock *db, u64 bytes, const u8 *snap) {
@@ -76,55 +131,64 @@ __global__ void k_init_seqtab(DecBlock *db, u64 bytes, const u8 *snap) {
         t[i] = s ? s[i] : 0x03030303u;
 }
 
-// decodeSymbol (inlined e.g. @0x42a7d0-0x42a960) on a warp model; every lane returns the symbol.
-// rc is warp-uniform (all lanes carry the same coder state).
-template <int N, int EPL>
-SQ_D u32 wm_decode(u32 *mp, RcDec &rc, int lane) {
-    u32 w[EPL];
+// decodeSymbol (inlined e.g. @0x42a7d0-0x42a960) on a warp model, in three phases so that the
+// caller can issue the NEXT model's loads between the search and the write-back of this one.
+template <int EPL> struct WReg { u32 w[EPL]; u32 bt, m32; };
+
+template <int EPL>
+SQ_D void wm_load(WReg<EPL> &R, const u32 *mp, int lane) {
 #pragma unroll
-    for (int i = 0; i < EPL; i++) w[i] = mp[i * 32 + lane];
-    u32 bt = mp[EPL * 32 + lane];
-    u32 base = bt & 0xffffu, tot = bt >> 16;
-    u32 bub = (w[0] >> 8) & 0xff;
-    w[0] &= 0xffff00ffu;
-    rc.range /= tot;
-    u32 r = rc.range, code = rc.code;
-    // lane-local search: first entry whose inclusive cumulative frequency * r exceeds code
-    int li = -1;
-    u32 c = base, cex = 0;
+    for (int i = 0; i < EPL; i++) R.w[i] = mp[i * 32 + lane];
+    R.bt = mp[EPL * 32 + lane];
+    R.m32 = mp[(EPL + 1) * 32 + lane];
+}
+
+// search + coder step; rc is warp-uniform.  Returns the symbol on every lane; kl / li locate it.
+template <int N, int EPL>
+SQ_D u32 wm_search(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li) {
+    u32 base = R.bt & 0xffffu, tot = R.bt >> 16;
+    u32 q = __umulhi(rc.range, R.m32);
+    if (rc.range - q * tot >= tot) q++;
+    rc.range = q;
+    u32 code = rc.code;
+    li = -1;
+    u32 c = base, cex = 0, wsel = 0;
 #pragma unroll
     for (int i = 0; i < EPL; i++) {
-        u32 cn = c + (w[i] >> 16);
-        if (li < 0 && code < cn * r) { li = i; cex = c; }
+        u32 cn = c + (R.w[i] >> 16);
+        bool h = (li < 0) && (code < cn * q);
+        if (h) { li = i; cex = c; wsel = R.w[i]; }
         c = cn;
     }
     u32 bal = __ballot_sync(FULL, li >= 0);
-    int kl;
     if (bal) kl = __ffs(bal) - 1;
     else {                                   // code beyond tot * r: corrupt stream; take the last symbol
         kl = (N - 1) / EPL;
-        if (lane == kl) { li = (N - 1) % EPL; cex = c - (w[(N - 1) % EPL] >> 16); }
+        if (lane == kl) { li = (N - 1) % EPL; wsel = R.w[(N - 1) % EPL]; cex = c - (wsel >> 16); }
     }
-    u32 wsel = 0;
-#pragma unroll
-    for (int i = 0; i < EPL; i++) if (i == li) wsel = w[i];
     wsel = __shfl_sync(FULL, wsel, kl);
     cex = __shfl_sync(FULL, cex, kl);
-    u32 sym = wsel & 0xff, freq = wsel >> 16;
-    rc.decode(cex, freq);
-    // model update (Freq += 8, TotFreq += 8, halve above 0xffe0, bubble swap every 16th symbol)
+    rc.decode(cex, wsel >> 16);
+    return wsel & 0xff;
+}
+
+// model update (Freq += 8, TotFreq += 8, halve above 0xffe0, bubble swap every 16th symbol) and
+// write-back; R is left holding the updated model.
+template <int N, int EPL>
+SQ_D void wm_update_store(u32 *mp, WReg<EPL> &R, int kl, int li, int lane) {
+    u32 base = R.bt & 0xffffu, tot = R.bt >> 16;
+    u32 bub = (R.w[0] >> 8) & 0xff;
+    R.w[0] &= 0xffff00ffu;
     bool mine = lane == kl;
-    if (mine) {
 #pragma unroll
-        for (int i = 0; i < EPL; i++) if (i == li) w[i] += 8u << 16;
-    }
-    if (lane > kl) base += 8;
+    for (int i = 0; i < EPL; i++) R.w[i] += (mine && i == li) ? (8u << 16) : 0u;
+    base += (lane > kl) ? 8u : 0u;
     tot += 8;
     bool all = false;
     if (tot > 0xffe0u) {
         u32 T = 0;
 #pragma unroll
-        for (int i = 0; i < EPL; i++) { u32 f = w[i] >> 16; f -= f >> 1; w[i] = (w[i] & 0xffffu) | (f << 16); T += f; }
+        for (int i = 0; i < EPL; i++) { u32 f = R.w[i] >> 16; f -= f >> 1; R.w[i] = (R.w[i] & 0xffffu) | (f << 16); T += f; }
         u32 inc = warp_incl_scan_d(T, lane);
         base = inc - T;
         tot = __shfl_sync(FULL, inc, 31);
@@ -133,12 +197,12 @@ SQ_D u32 wm_decode(u32 *mp, RcDec &rc, int lane) {
     bub = (bub + 1) & 0xff;
     bool prevlane = false;
     if ((bub & 15) == 0) {
-        u32 up = __shfl_up_sync(FULL, w[EPL - 1], 1);
+        u32 up = __shfl_up_sync(FULL, R.w[EPL - 1], 1);
         u32 cur = 0, prv = up;
 #pragma unroll
         for (int i = 0; i < EPL; i++) {
-            if (i == li) cur = w[i];
-            if (i + 1 == li) prv = w[i];
+            if (i == li) cur = R.w[i];
+            if (i + 1 == li) prv = R.w[i];
         }
         bool dosw = mine && (kl * EPL + li > 0) && (cur >> 16) > (prv >> 16);
         u32 swb = __ballot_sync(FULL, dosw);
@@ -146,23 +210,34 @@ SQ_D u32 wm_decode(u32 *mp, RcDec &rc, int lane) {
             int lik = __shfl_sync(FULL, li, kl);
             u32 cw = __shfl_sync(FULL, cur, kl), pw = __shfl_sync(FULL, prv, kl);
             if (lik > 0) {
-                if (mine) {
 #pragma unroll
-                    for (int i = 1; i < EPL; i++) if (i == li) { w[i] = pw; w[i - 1] = cw; }
-                }
+                for (int i = 1; i < EPL; i++) if (mine && i == li) { R.w[i] = pw; R.w[i - 1] = cw; }
             } else {
-                if (mine) { w[0] = pw; base += (cw >> 16) - (pw >> 16); }
-                if (lane == kl - 1) { w[EPL - 1] = cw; prevlane = true; }
+                if (mine) { R.w[0] = pw; base += (cw >> 16) - (pw >> 16); }
+                if (lane == kl - 1) { R.w[EPL - 1] = cw; prevlane = true; }
             }
         }
     }
-    // write back: row 0 carries bub and the base row carries tot, so both are rewritten by every lane
-    mp[lane] = w[0] | (bub << 8);
-    mp[EPL * 32 + lane] = base | (tot << 16);
+    R.w[0] |= bub << 8;
+    R.bt = base | (tot << 16);
+    R.m32 = recip32(tot);
+    // row 0 carries bub, the base row tot, the last row its reciprocal: rewritten by every lane
+    mp[lane] = R.w[0];
+    mp[EPL * 32 + lane] = R.bt;
+    mp[(EPL + 1) * 32 + lane] = R.m32;
     if (mine || prevlane || all) {
 #pragma unroll
-        for (int i = 1; i < EPL; i++) mp[i * 32 + lane] = w[i];
+        for (int i = 1; i < EPL; i++) mp[i * 32 + lane] = R.w[i];
     }
+}
+
+template <int N, int EPL>
+SQ_D u32 wm_decode(u32 *mp, RcDecW &rc, int lane) {
+    WReg<EPL> R;
+    wm_load(R, mp, lane);
+    int kl, li;
+    u32 sym = wm_search<N, EPL>(R, rc, lane, kl, li);
+    wm_update_store<N, EPL>(mp, R, kl, li, lane);
     return sym;
 }
 
@@ -201,12 +276,17 @@ __global__ void __launch_bounds__(32) k_dec_len(DecBlock *db) {
 // are warp models, last_name / the name being built live in shared memory.
 struct NameSmem { u8 last[1024]; u8 cur[256]; };
 
-SQ_D int decode_name(DecBlock &d, RcDec &rc, u8 *name_out, u64 room, NameSmem &ns, int &lnl, int &lpl, int &lsl, int lane) {
-    u32 *prefix = d.nametab, *suffix = prefix + 256 * W256_STRIDE, *lenm = suffix + 256 * W256_STRIDE;
+SQ_D int decode_name(u32 *nametab, RcDecW &rc, u8 *name_out, u64 room, NameSmem &ns, int &lnl, int &lpl, int &lsl, int lane) {
+    u32 *prefix = nametab, *suffix = prefix + 256 * W256_STRIDE, *lenm = suffix + 256 * W256_STRIDE;
     u32 *middle = lenm + 256 * W256_STRIDE;
-    int p = (int)wm_decode<256, 8>(prefix + (u64)lpl * W256_STRIDE, rc, lane);
-    int s = (int)wm_decode<256, 8>(suffix + (u64)lsl * W256_STRIDE, rc, lane);
-    int n = (int)wm_decode<256, 8>(lenm + (u64)lnl * W256_STRIDE, rc, lane);
+    // the three header models of a read are known up front: fetch them together
+    WReg<8> Rp, Rs, Rl;
+    u32 *mpp = prefix + (u64)lpl * W256_STRIDE, *mps = suffix + (u64)lsl * W256_STRIDE, *mpl = lenm + (u64)lnl * W256_STRIDE;
+    wm_load(Rp, mpp, lane); wm_load(Rs, mps, lane); wm_load(Rl, mpl, lane);
+    int kl, li;
+    int p = (int)wm_search<256, 8>(Rp, rc, lane, kl, li); wm_update_store<256, 8>(mpp, Rp, kl, li, lane);
+    int s = (int)wm_search<256, 8>(Rs, rc, lane, kl, li); wm_update_store<256, 8>(mps, Rs, kl, li, lane);
+    int n = (int)wm_search<256, 8>(Rl, rc, lane, kl, li); wm_update_store<256, 8>(mpl, Rl, kl, li, lane);
     lpl = p; lsl = s;
     if ((u64)n > room) return -1;                                          // caller's ID buffer is full
     if (p > n || s > n - p || s > lnl) { p = p > n ? n : p; s = 0; }       // corrupt stream guard
@@ -239,30 +319,41 @@ SQ_D int decode_name(DecBlock &d, RcDec &rc, u8 *name_out, u64 room, NameSmem &n
     return n;
 }
 
-// decode_qual @0x42a750 (whole warp, uniform)
-SQ_D void decode_qual(DecBlock &d, RcDec &rc, u8 *q, int len, int qlevel, int lane) {
-    u32 *tab = d.qualtab;
-    u32 last = 0, delta = 5, q1 = 0, q2 = 0;
-    for (int i = 0; i < len; i++) {
-        u32 qq = wm_decode<95, 3>(tab + (u64)last * WQ_STRIDE, rc, lane);
-        if (qq == 94) { for (int t = i + lane; t < len; t += 32) q[t] = '#'; return; }
-        if (lane == 0) q[i] = (u8)(qq + 33);
-        if (q1 > qq) delta += q1 - qq;
-        last = qual_ctx(qq, q1, q2, delta, qlevel, i);
-        q2 = q1; q1 = qq;
-    }
-}
+// one base (inlined four times in decode_seq @0x4296b0); whole warp, uniform.
+// The 256 contexts reachable in four more bases are one contiguous KiB of the table: every step
+// the warp copies that KiB asynchronously (cp.async, L2 -> shared) into an 8-slot ring and reads
+// the counters it needs NOW from the slot filled four steps ago, so the table's L2 / HBM latency is
+// off the symbol chain.  Counters updated during those four steps are forwarded from a 4-entry log.
+// Every lane stores the updated counters (same value, same address): each lane later reads its own
+// store, and __syncwarp orders it before the other lanes' later copies.
+struct SeqPipe {
+    u32 step;
+    u32 lc0, lc1, lc2, lc3, lv0, lv1, lv2, lv3;      // last four updated (context, counters), 0 = newest
+    SQ_D void init() { step = 0; lc0 = lc1 = lc2 = lc3 = 0xffffffffu; lv0 = lv1 = lv2 = lv3 = 0; }
+};
 
-// one base (inlined four times in decode_seq @0x4296b0); whole warp, uniform.  Every lane stores
-// the updated counters (same value, same address) so that each lane later reads its own store.
-// The 256 contexts reachable in four more bases are one contiguous KiB: lanes 0..7 prefetch it.
-SQ_D u32 decode_base(u8 *seqtab, RcDec &rc, u32 &last, u32 mask, int lane) {
-    if (lane < 8) {
-        const u8 *pf = seqtab + ((u64)((last << 8) & mask) << 2) + lane * 128;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+SQ_D u32 decode_base(u8 *seqtab, u32 *ring, RcDecW &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane) {
+    {
+        u32 base4 = (last << 8) & mask;
+        const u8 *src = seqtab + ((u64)base4 << 2) + lane * 32;
+        u32 dst = (u32)__cvta_generic_to_shared(ring + ((P.step + 4) & 7) * 256 + lane * 8);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                     "cp.async.cg.shared.global [%2], [%3], 16;\n"
+                     "cp.async.commit_group;\n" ::"r"(dst), "l"(src), "r"(dst + 16), "l"(src + 16) : "memory");
     }
     u32 *S4 = (u32 *)(seqtab + (u64)last * 4);
-    u32 x = *S4;
+    u32 x;
+    if (nb >= 4) {
+        asm volatile("cp.async.wait_group 4;\n" ::: "memory");
+        __syncwarp();
+        x = ring[(P.step & 7) * 256 + (last & 255)];
+    } else {
+        x = *S4;
+    }
+    if (P.lc3 == last) x = P.lv3;
+    if (P.lc2 == last) x = P.lv2;
+    if (P.lc1 == last) x = P.lv1;
+    if (P.lc0 == last) x = P.lv0;
     u32 S0 = x & 0xff, S1 = (x >> 8) & 0xff, S2 = (x >> 16) & 0xff, S3 = x >> 24;
     u32 tot = S0 + S1 + S2 + S3;
     if (tot > 253) { S0 -= S0 >> 1; S1 -= S1 >> 1; S2 -= S2 >> 1; S3 -= S3 >> 1; tot = S0 + S1 + S2 + S3; }
@@ -275,7 +366,11 @@ SQ_D u32 decode_base(u8 *seqtab, RcDec &rc, u32 &last, u32 mask, int lane) {
     else { b = 3; cum = S0 + S1 + S2; f = S3; }
     rc.decode(cum, f);
     if (b == 0) S0 = (S0 + 1) & 0xff; else if (b == 1) S1 = (S1 + 1) & 0xff; else if (b == 2) S2 = (S2 + 1) & 0xff; else S3 = (S3 + 1) & 0xff;
-    *S4 = S0 | (S1 << 8) | (S2 << 16) | (S3 << 24);
+    u32 nv = S0 | (S1 << 8) | (S2 << 16) | (S3 << 24);
+    *S4 = nv;
+    __syncwarp();
+    P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
+    P.step++;
     last = (last * 4 + b) & mask;
     return b;
 }
@@ -311,6 +406,7 @@ struct KModelD {
     }
 };
 struct MainSmem {
+    u32 ring[8 * 256];         // base-model candidate ring of the seq warp
     NameSmem ns;
     SmModel<2> tip;
     SmModel<11> ch;
@@ -322,39 +418,83 @@ struct MainSmem {
 };
 
 __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int qlevel, int id_rule, u32 seqmask) {
-    __shared__ MainSmem sm;
+    __shared__ __align__(16) MainSmem sm;
     DecBlock &d = db[blockIdx.x];
     int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { sm.qprog = 0; sm.side_err = 0; }
     __syncthreads();
     if (d.status != 0) return;
     const char tbl[] = "ACGT";
+#ifdef SQ_DEBUG_TIMING
+    long long t_begin = clock64();
+#define SQ_TICK(name) if (blockIdx.x == 0 && lane == 0) printf("dec warp %d %s: %lld cycles\n", wid, name, clock64() - t_begin)
+#else
+#define SQ_TICK(name)
+#endif
+    const u32 nreads = d.nreads;
+    const u8 *rec = d.rec;
+    const u32 *seqoff = d.seqoff;
+    const i32 *seqlen = d.seqlen;
     if (wid == 0) {                                            // names (decompressName @0x428ca0)
         if (id_rule) { if (lane == 0) d.status = SQ_ERR_FORMAT_K; return; }   // rule-based IDs: regenerated on the host ("next" row)
         for (int i = lane; i < 1024; i += 32) sm.ns.last[i] = ' ';
         __syncwarp();
         int lnl = 0, lpl = 0, lsl = 0;
-        RcDec rc;
-        rc.start(d.rec + d.off[5], d.rec + d.off[5] + d.len[5]);
+        RcDecW rc;
+        rc.start(rec + d.off[5], rec + d.off[5] + d.len[5]);
         u64 o = 0;
-        for (u32 r = 0; r < d.nreads; r++) {
-            int n = decode_name(d, rc, d.ids + o, d.idcap - o, sm.ns, lnl, lpl, lsl, lane);
+        u32 *nametab = d.nametab;
+        u8 *ids = d.ids;
+        u16 *idlen = d.idlen;
+        const u64 idcap = d.idcap;
+        for (u32 r = 0; r < nreads; r++) {
+            int n = decode_name(nametab, rc, ids + o, idcap - o, sm.ns, lnl, lpl, lsl, lane);
             if (n < 0) { if (lane == 0) d.status = SQ_ERR_CAPACITY_K; return; }
-            if (lane == 0) d.idlen[r] = (u16)n;
+            if (lane == 0) idlen[r] = (u16)n;
             o += (u32)n;
         }
         if (lane == 0) d.idbytes = o;
-    } else if (wid == 1) {                                     // qualities (decompressQual @0x42aa40)
-        RcDec rc;
-        rc.start(d.rec + d.off[7], d.rec + d.off[7] + d.len[7]);
-        for (u32 r = 0; r < d.nreads; r++) {
-            decode_qual(d, rc, d.qual + d.seqoff[r], d.seqlen[r], qlevel, lane);
-            if ((r & 15) == 15 || r + 1 == d.nreads) {
+        SQ_TICK("names");
+    } else if (wid == 1) {                                     // qualities (decompressQual @0x42aa40, decode_qual @0x42a750)
+        RcDecW rc;
+        rc.start(rec + d.off[7], rec + d.off[7] + d.len[7]);
+        u32 *tab = d.qualtab;
+        u8 *qual = d.qual;
+        WReg<3> R;
+        u32 last = 0;
+        wm_load(R, tab, lane);                                 // context 0 opens every read
+        for (u32 r = 0; r < nreads; r++) {
+            u8 *q = qual + seqoff[r];
+            int len = seqlen[r];
+            u32 delta = 5, q1 = 0, q2 = 0;
+            for (int i = 0; i < len; i++) {
+                int kl, li;
+                u32 qq = wm_search<95, 3>(R, rc, lane, kl, li);
+                u32 nlast = 0;
+                bool term = qq == 94;
+                if (!term) {
+                    if (lane == 0) q[i] = (u8)(qq + 33);
+                    if (q1 > qq) delta += q1 - qq;
+                    if (i + 1 < len) nlast = qual_ctx(qq, q1, q2, delta, qlevel, i);
+                    q2 = q1; q1 = qq;
+                }
+                // the next model's rows are requested before this model is written back
+                u32 *mp = tab + (u64)last * WQ_STRIDE;
+                WReg<3> Rn;
+                bool same = nlast == last;
+                if (!same) wm_load(Rn, tab + (u64)nlast * WQ_STRIDE, lane);
+                wm_update_store<95, 3>(mp, R, kl, li, lane);
+                if (!same) R = Rn;
+                last = nlast;
+                if (term) { for (int t = i + lane; t < len; t += 32) q[t] = '#'; break; }
+            }
+            if ((r & 15) == 15 || r + 1 == nreads) {
                 __syncwarp();
                 __threadfence_block();
                 if (lane == 0) sm.qprog = r + 1;
             }
         }
+        SQ_TICK("qual");
     } else {                                                   // Dege streams, then bases (decompressSeq @0x42e390)
         if (lane == 0) {
             u32 n_tip = dec_small<2>(d, 23, sm.tip, d.d_tip, d.nreads, 0);
@@ -380,54 +520,64 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int qlevel, int i
         }
         __syncwarp();
         if (sm.side_err) { if (lane == 0) d.status = SQ_ERR_FORMAT_K; return; }
+        SQ_TICK("dege");
         u32 n_tip = sm.cnts[0], n_ch = sm.cnts[1], n_mq = sm.cnts[2], n_cnt = sm.cnts[3], n_pos = sm.cnts[4];
         // the Dege arrays were written by lane 0: the other lanes read them through L2
-        RcDec rc;
-        rc.start(d.rec + d.off[6], d.rec + d.off[6] + d.len[6]);
+        const u8 *d_tip = d.d_tip, *d_ch = d.d_ch, *d_maxq = d.d_maxq;
+        const u32 *d_cnt = d.d_cnt, *d_pos = d.d_pos;
+        u8 *seqtab = d.seqtab, *seqout = d.seq;
+        const u8 *qualbuf = d.qual;
+        RcDecW rc;
+        rc.start(rec + d.off[6], rec + d.off[6] + d.len[6]);
+        SeqPipe P;
+        P.init();
         u32 i_mq = 0, i_ch = 0, i_pos = 0;
-        for (u32 r = 0; r < d.nreads; r++) {
-            u8 *seq = d.seq + d.seqoff[r];
-            int len = d.seqlen[r];
+        for (u32 r = 0; r < nreads; r++) {
+            u8 *seq = seqout + seqoff[r];
+            int len = seqlen[r];
             u32 last = 0x7616c7u & seqmask;
-            bool flagged = r < n_tip && __ldcg(d.d_tip + r);
+            u32 nb = 0;
+            bool flagged = r < n_tip && __ldcg(d_tip + r);
             if (!flagged) {
                 for (int i = 0; i < len; i++) {
-                    u32 bb = decode_base(d.seqtab, rc, last, seqmask, lane);
+                    u32 bb = decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane);
                     if (lane == 0) seq[i] = (u8)tbl[bb];
                 }
                 continue;
             }
             while (sm.qprog <= r) __nanosleep(200);            // this read's qualities place its N bases
             __threadfence_block();
-            const u8 *qual = d.qual + d.seqoff[r];
+            const u8 *qual = qualbuf + seqoff[r];
             if (i_mq >= n_mq) { if (lane == 0) d.status = SQ_ERR_FORMAT_K; return; }
-            int mq = (int)(int8_t)__ldcg(d.d_maxq + i_mq);
-            u32 cnt = i_mq < n_cnt ? __ldcg(d.d_cnt + i_mq) : 0;
+            int mq = (int)(int8_t)__ldcg(d_maxq + i_mq);
+            u32 cnt = i_mq < n_cnt ? __ldcg(d_cnt + i_mq) : 0;
             i_mq++;
             if (cnt == 0) {                                    // @0x429a20: every candidate position is non-ACGT
                 for (int i = 0; i < len; i++) {
                     u32 c;
-                    if (mq >= (int)(int8_t)__ldcg(qual + i)) { c = i_ch < n_ch ? __ldcg(d.d_ch + i_ch) : 'N'; i_ch++; }
-                    else c = (u8)tbl[decode_base(d.seqtab, rc, last, seqmask, lane)];
+                    if (mq >= (int)(int8_t)__ldcg(qual + i)) { c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
+                    else c = (u8)tbl[decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane)];
                     if (lane == 0) seq[i] = (u8)c;
                 }
                 continue;
             }
-            u32 gap = i_pos < n_pos ? __ldcg(d.d_pos + i_pos) : 0, remaining = cnt - 1, run = 0;   // @0x4298cc
+            u32 gap = i_pos < n_pos ? __ldcg(d_pos + i_pos) : 0, remaining = cnt - 1, run = 0;   // @0x4298cc
             i_pos++;
             for (int i = 0; i < len; i++) {
                 u32 c;
                 if (mq >= (int)(int8_t)__ldcg(qual + i)) {
                     if (run == gap) {                          // @0x429b40
                         gap = 0xffffffffu;
-                        if (remaining) { remaining--; gap = i_pos < n_pos ? __ldcg(d.d_pos + i_pos) : 0; i_pos++; }
-                        c = (u8)tbl[decode_base(d.seqtab, rc, last, seqmask, lane)];
+                        if (remaining) { remaining--; gap = i_pos < n_pos ? __ldcg(d_pos + i_pos) : 0; i_pos++; }
+                        c = (u8)tbl[decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane)];
                         run = 0;
-                    } else { run++; c = i_ch < n_ch ? __ldcg(d.d_ch + i_ch) : 'N'; i_ch++; }
-                } else c = (u8)tbl[decode_base(d.seqtab, rc, last, seqmask, lane)];
+                    } else { run++; c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
+                } else c = (u8)tbl[decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane)];
                 if (lane == 0) seq[i] = (u8)c;
             }
         }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        SQ_TICK("seq");
     }
 }
 
