@@ -28,26 +28,29 @@ struct Arena {
 };
 
 struct StageTimer {
-    std::vector<const char *> names;
-    std::vector<cudaEvent_t> ev;       // ev[i] .. ev[i+1] brackets names[i]
+    struct Span { const char *name; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;           // pool; first `n` are live for the current wave
     std::vector<std::pair<const char *, float>> acc;
     size_t n = 0;
-    void begin(cudaStream_t st) { n = 0; names.clear(); mark(nullptr, st); }
-    void mark(const char *name, cudaStream_t st) {
-        if (n == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
-        cudaEventRecord(ev[n++], st);
-        if (name) names.push_back(name);
+    void begin_wave() { n = 0; }
+    // open a span on `st`; returns its index
+    size_t open(const char *name, cudaStream_t st) {
+        if (n == spans.size()) { Span sp{}; cudaEventCreate(&sp.e0); cudaEventCreate(&sp.e1); spans.push_back(sp); }
+        spans[n].name = name;
+        cudaEventRecord(spans[n].e0, st);
+        return n++;
     }
-    void collect() {       // after a stream sync
-        for (size_t i = 0; i < names.size(); i++) {
+    void close(size_t i, cudaStream_t st) { cudaEventRecord(spans[i].e1, st); }
+    void collect() {       // after the streams were synchronised
+        for (size_t i = 0; i < n; i++) {
             float ms = 0;
-            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            cudaEventElapsedTime(&ms, spans[i].e0, spans[i].e1);
             bool found = false;
-            for (auto &a : acc) if (a.first == names[i]) { a.second += ms; found = true; break; }
-            if (!found) acc.push_back({names[i], ms});
+            for (auto &a : acc) if (a.first == spans[i].name) { a.second += ms; found = true; break; }
+            if (!found) acc.push_back({spans[i].name, ms});
         }
     }
-    void destroy() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); }
+    void destroy() { for (auto &sp : spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); } spans.clear(); }
 };
 
 }  // namespace
@@ -57,6 +60,8 @@ struct sq_ctx {
     int nsm = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // md5, side, rc x 3 run beside the main stream
+    cudaEvent_t ev[8] = {};
     Arena arena;
     std::string err;
     // model snapshot
@@ -123,6 +128,10 @@ extern "C" int sq_create(const sq_params *p, sq_ctx **out) {
         if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
         c->own_stream = true;
     }
+    for (int i = 0; i < 5; i++)
+        if ((e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
+    for (int i = 0; i < 8; i++)
+        if ((e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
     u64 want = p->workspace_bytes;
     if (want == 0) {
         size_t fr = 0, tot = 0;
@@ -141,6 +150,8 @@ extern "C" void sq_destroy(sq_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->p.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 5; i++) if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
+    for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     c->timer.destroy();
     if (c->arena.base) cudaFree(c->arena.base);
     if (c->d_model) cudaFree(c->d_model);
@@ -327,7 +338,8 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     if (!ok) { c->err = "internal: wave does not fit the workspace"; return SQ_ERR_NOMEM; }
 
     StageTimer &T = c->timer;
-    T.begin(st);
+    T.begin_wave();
+    size_t sp = T.open("h2d", st);
     if (host) {
         for (int i = 0; i < n; i++) {
             const sq_block_in &b = blocks[i];
@@ -349,35 +361,67 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     CUDA_OK(c, cudaMemcpyAsync(w.bd, bd.data(), sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, st));
     CUDA_OK(c, cudaMemcpyAsync(w.rbase, rbase.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
     CUDA_OK(c, cudaMemsetAsync(w.bs, 0, sizeof(BlockState) * n, st));
-    T.mark("h2d", st);
+    T.close(sp, st);
 
+    // The serial chain kernels (MD5, side streams, one range-coder pass per stream) each use a
+    // handful of warps for a long time; they run on their own streams beside the parallel
+    // context / sort / replay kernels of the main stream and are joined before the pack.
     u64 *L = &c->launches;
+    cudaStream_t s_md5 = c->aux[0], s_side = c->aux[1];
+    CUDA_OK(c, cudaEventRecord(c->ev[0], st));                       // inputs resident
+    CUDA_OK(c, cudaStreamWaitEvent(s_md5, c->ev[0], 0));
+    sp = T.open("md5", s_md5);
+    CUDA_OK(c, sqk_md5(w, s_md5, L));
+    T.close(sp, s_md5);
+    CUDA_OK(c, cudaEventRecord(c->ev[1], s_md5));
+
+    sp = T.open("count", st);
     CUDA_OK(c, sqk_prep(w, st, L));
-    if (c->p.lossy) { CUDA_OK(c, sqk_rblock(w, c->p.lossy_r, st, L)); T.mark("rblock", st); }
+    if (c->p.lossy) CUDA_OK(c, sqk_rblock(w, c->p.lossy_r, st, L));
     CUDA_OK(c, sqk_count(w, st, L));
-    T.mark("count", st);
-    CUDA_OK(c, sqk_md5(w, st, L));
-    T.mark("md5", st);
-    CUDA_OK(c, sqk_side(w, st, L));
-    T.mark("side", st);
+    T.close(sp, st);
+    CUDA_OK(c, cudaEventRecord(c->ev[2], st));                       // per-read offsets, tip flags, counts
+    CUDA_OK(c, cudaStreamWaitEvent(s_side, c->ev[2], 0));
+    sp = T.open("side", s_side);
+    CUDA_OK(c, sqk_side(w, s_side, L));
+    T.close(sp, s_side);
+    CUDA_OK(c, cudaEventRecord(c->ev[3], s_side));
+
     static const char *nm_emit[3] = {"seq.ctx", "qual.ctx", "name.ctx"};
     static const char *nm_sort[3] = {"seq.sort", "qual.sort", "name.sort"};
     static const char *nm_rep[3] = {"seq.replay", "qual.replay", "name.replay"};
+    static const char *nm_rc[3] = {"seq.rc", "qual.rc", "name.rc"};
     int keybits[3] = {(int)(2 * c->NS()), c->p.qlevel > 2 ? 20 : 16, 14};
-    for (int s = 0; s < ST_COUNT; s++) {
-        if (s == ST_NAME && c->p.id_rule) continue;
-        CUDA_OK(c, sqk_emit(w, s, w.elemA, st, L));
-        T.mark(nm_emit[s], st);
-        u64 *sorted = nullptr;
-        CUDA_OK(c, sqk_sort(w, s, keybits[s], w.elemA, w.elemB, &sorted, st, L));
-        T.mark(nm_sort[s], st);
-        CUDA_OK(c, sqk_replay(w, s, sorted, w.triples[s], st, L));
-        T.mark(nm_rep[s], st);
+    // quality first: its replay + range-coder chain is the longest
+    const int order[3] = {ST_QUAL, ST_SEQ, ST_NAME};
+    for (int oi = 0; oi < 3; oi++) {
+        int s = order[oi];
+        cudaStream_t s_rc = c->aux[2 + s];
+        if (!(s == ST_NAME && c->p.id_rule)) {
+            sp = T.open(nm_emit[s], st);
+            CUDA_OK(c, sqk_emit(w, s, w.elemA, st, L));
+            T.close(sp, st);
+            u64 *sorted = nullptr;
+            sp = T.open(nm_sort[s], st);
+            CUDA_OK(c, sqk_sort(w, s, keybits[s], w.elemA, w.elemB, &sorted, st, L));
+            T.close(sp, st);
+            sp = T.open(nm_rep[s], st);
+            CUDA_OK(c, sqk_replay(w, s, sorted, w.triples[s], st, L));
+            T.close(sp, st);
+        }
+        CUDA_OK(c, cudaEventRecord(c->ev[4 + s], st));
+        CUDA_OK(c, cudaStreamWaitEvent(s_rc, c->ev[4 + s], 0));
+        sp = T.open(nm_rc[s], s_rc);
+        CUDA_OK(c, sqk_rc(w, s, s_rc, L));
+        T.close(sp, s_rc);
+        CUDA_OK(c, cudaEventRecord(c->ev[4 + s], s_rc));
     }
-    CUDA_OK(c, sqk_rc(w, st, L));
-    T.mark("rc", st);
+    CUDA_OK(c, cudaStreamWaitEvent(st, c->ev[1], 0));
+    CUDA_OK(c, cudaStreamWaitEvent(st, c->ev[3], 0));
+    for (int s = 0; s < 3; s++) CUDA_OK(c, cudaStreamWaitEvent(st, c->ev[4 + s], 0));
+    sp = T.open("pack", st);
     CUDA_OK(c, sqk_pack(w, host ? 1 : 0, st, L));
-    T.mark("pack", st);
+    T.close(sp, st);
 
     // ---- results
     u64 small = sizeof(BlockState) * (u64)n + 8 * ((u64)n + 1);
@@ -388,6 +432,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     CUDA_OK(c, cudaMemcpyAsync(hbs, w.bs, sizeof(BlockState) * n, cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaMemcpyAsync(hoff, w.recoff, 8 * ((u64)n + 1), cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaStreamSynchronize(st));
+    size_t sp_d2h = host ? T.open("d2h", st) : 0;
     int worst = SQ_OK;
     for (int i = 0; i < n; i++) {
         out[i].status = hbs[i].status;
@@ -398,7 +443,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
         }
         if (out[i].status != 0 && worst == 0) worst = out[i].status;
     }
-    if (host) { T.mark("d2h", st); CUDA_OK(c, cudaStreamSynchronize(st)); }
+    if (host) { T.close(sp_d2h, st); CUDA_OK(c, cudaStreamSynchronize(st)); }
     T.collect();
     c->last = w; c->last_bd = bd; c->last_valid = true;
     if (worst) c->err = "one or more blocks failed; see per-block status";
@@ -601,19 +646,22 @@ int decode_wave(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_
     }
     if (!ok) { c->err = "internal: decode wave does not fit the workspace"; return SQ_ERR_NOMEM; }
     StageTimer &T = c->timer;
-    T.begin(st);
+    T.begin_wave();
+    size_t sp = T.open("h2d", st);
     if (host)
         for (int i = 0; i < n; i++)
             if (!db[i].status) CUDA_OK(c, cudaMemcpyAsync((void *)db[i].rec, recs[i], reclens[i], cudaMemcpyHostToDevice, st));
     CUDA_OK(c, cudaMemcpyAsync(w.db, db.data(), sizeof(DecBlock) * n, cudaMemcpyHostToDevice, st));
-    T.mark("h2d", st);
+    T.close(sp, st);
+    sp = T.open("decode", st);
     CUDA_OK(c, sqk_decode(w, st, &c->launches));
-    T.mark("decode", st);
+    T.close(sp, st);
     int rc = ensure_pin(c, sizeof(DecBlock) * (u64)n);
     if (rc) return rc;
     DecBlock *hdb = (DecBlock *)c->h_pin;
     CUDA_OK(c, cudaMemcpyAsync(hdb, w.db, sizeof(DecBlock) * n, cudaMemcpyDeviceToHost, st));
     CUDA_OK(c, cudaStreamSynchronize(st));
+    size_t sp_d2h = host ? T.open("d2h", st) : 0;
     int worst = SQ_OK;
     for (int i = 0; i < n; i++) {
         sq_block_dec &o = out[i];
@@ -631,7 +679,7 @@ int decode_wave(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_
         }
         if (o.status && !worst) worst = o.status;
     }
-    if (host) { T.mark("d2h", st); CUDA_OK(c, cudaStreamSynchronize(st)); }
+    if (host) { T.close(sp_d2h, st); CUDA_OK(c, cudaStreamSynchronize(st)); }
     T.collect();
     if (worst) c->err = "one or more blocks failed to decode; see per-block status";
     return worst;

@@ -588,7 +588,12 @@ __global__ void __launch_bounds__(128) k_replay_warp(const u64 *src, const Block
 //          shift count.  The carry-less range adjustment (@0x422040-0x422058) fires about once
 //          per 2^32 renormalisations; it is DETECTED on the fast path, and the 32-symbol group is
 //          then rolled back and re-run with the exact loop.
-#define RC_NBUF 4
+#ifndef RC_NBUF
+#define RC_NBUF 8
+#endif
+#ifndef RC_SLEEP
+#define RC_SLEEP 0
+#endif
 struct RcState { u64 low; u32 range; u32 nout; };
 
 SQ_D void rc_exact_step(RcState &s, u8 *out, u32 cum, u32 freq, u32 tot) {
@@ -627,27 +632,35 @@ SQ_D void rc_exact_step(RcState &s, u8 *out, u32 cum, u32 freq, u32 tot) {
     }
 
 __global__ void __launch_bounds__(64) k_rc(const BlockDesc *bd, BlockState *bs, const u64 *tr_seq, const u64 *tr_qual,
-                                           const u64 *tr_name, u8 *obuf, int skip_name) {
+                                           const u64 *tr_name, u8 *obuf, int skip_name, int st) {
     __shared__ uint4 rec[RC_NBUF][32];
     __shared__ volatile u32 produced, consumed;
-    int b = blockIdx.x, st = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (st == ST_NAME && skip_name) return;
+    int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (st == ST_NAME && skip_name) {          // rule-based IDs: no name stream
+        if (threadIdx.x == 0) bs[b].olen[st] = 0;
+        return;
+    }
     const u64 *tr = (st == ST_SEQ ? tr_seq : st == ST_QUAL ? tr_qual : tr_name) + bd[b].ebase[st];
     u32 n = bs[b].nsym[st];
     u32 ngroups = (n + 31) / 32;
     if (threadIdx.x == 0) { produced = 0; consumed = 0; }
     __syncthreads();
     if (warp == 1) {
-        u64 t = (u32)lane < n ? tr[lane] : 0;
+        // triples are fetched three groups ahead of the one being prepared
+        u64 t0 = (u32)lane < n ? tr[lane] : 0;
+        u64 t1 = (u64)32 + lane < n ? tr[32 + lane] : 0;
+        u64 t2 = (u64)64 + lane < n ? tr[64 + lane] : 0;
         for (u32 g = 0; g < ngroups; g++) {
-            while (g >= consumed + RC_NBUF) __nanosleep(32);
+            u64 nx = (u64)(g + 3) * 32 + lane;
+            u64 t3 = nx < n ? tr[nx] : 0;
+            while (g >= consumed + RC_NBUF) { if (RC_SLEEP) __nanosleep(RC_SLEEP); }
+            u64 t = t0;
             u32 tot = (u32)(t >> 32) & 0xffffu;
             if (tot < 2) tot = 2;
             u64 M = ~(u64)0 / tot + 1;
             // x = M lo, y = M hi, z = cum | tot << 16, w = freq
             rec[g % RC_NBUF][lane] = make_uint4((u32)M, (u32)(M >> 32), ((u32)t & 0xffffu) | (tot << 16), (u32)(t >> 16) & 0xffffu);
-            u64 nx = (u64)(g + 1) * 32 + lane;
-            t = nx < n ? tr[nx] : 0;
+            t0 = t1; t1 = t2; t2 = t3;
             __threadfence_block();
             __syncwarp();
             if (lane == 0) produced = g + 1;
@@ -687,8 +700,8 @@ __global__ void __launch_bounds__(64) k_rc(const BlockDesc *bd, BlockState *bs, 
 // =============================================================================================
 // MD5 of the three input buffers of a block (calcBlockMd5 @0x414d90): one thread per buffer.
 __global__ void __launch_bounds__(32) k_md5(const BlockDesc *bd, BlockState *bs, int B) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3 * B) return;
+    int t = blockIdx.x;                       // one CTA (lane 0 of one warp) per buffer: chains must not share an issue slot
+    if (t >= 3 * B || threadIdx.x != 0) return;
     int b = t / 3, which = t % 3;
     const u8 *p = which == 0 ? bd[b].ids : which == 1 ? bd[b].seq : bd[b].qual;
     u64 n = which == 0 ? bd[b].idbytes : bd[b].seqbytes;
@@ -1102,20 +1115,20 @@ cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *tri
     return cudaGetLastError();
 }
 
-cudaError_t sqk_rc(const EncWave &w, cudaStream_t st, u64 *launches) {
-    k_rc<<<dim3(w.B, 3), 64, 0, st>>>(w.bd, w.bs, w.triples[ST_SEQ], w.triples[ST_QUAL], w.triples[ST_NAME], w.obuf, w.id_rule);
+cudaError_t sqk_rc(const EncWave &w, int stream, cudaStream_t st, u64 *launches) {
+    k_rc<<<w.B, 64, SQ_CHAIN_SMEM_RC, st>>>(w.bd, w.bs, w.triples[ST_SEQ], w.triples[ST_QUAL], w.triples[ST_NAME], w.obuf, w.id_rule, stream);
     *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t sqk_md5(const EncWave &w, cudaStream_t st, u64 *launches) {
-    k_md5<<<cdiv(3ull * w.B, 32), 32, 0, st>>>(w.bd, w.bs, w.B);
+    k_md5<<<3 * w.B, 32, SQ_CHAIN_SMEM_SMALL, st>>>(w.bd, w.bs, w.B);
     *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t sqk_side(const EncWave &w, cudaStream_t st, u64 *launches) {
-    k_side<<<w.B, 160, 0, st>>>(w.bd, w.bs, w.rbase, w.seqoff, w.tip, w.sidebuf);
+    k_side<<<w.B, 160, SQ_CHAIN_SMEM_SMALL, st>>>(w.bd, w.bs, w.rbase, w.seqoff, w.tip, w.sidebuf);
     *launches += 1;
     return cudaGetLastError();
 }
@@ -1128,7 +1141,14 @@ cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launch
     return cudaGetLastError();
 }
 
+// Chain kernels are launched on side streams while the main stream keeps every SM busy, and the
+// block scheduler then drops their CTAs onto whichever SM frees a slot first: without a limit two
+// dozen serial chains end up sharing one SM's four issue ports (measured: 6.6x slower).  Asking for
+// shared memory they do not use caps the chains per SM (227 KB / 72 KB = 3, / 36 KB = 6).
 cudaError_t sqk_enc_attrs() {
+    CK(cudaFuncSetAttribute(k_rc, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_RC));
+    CK(cudaFuncSetAttribute(k_md5, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_SMALL));
+    CK(cudaFuncSetAttribute(k_side, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_SMALL));
     CK(cudaFuncSetAttribute(k_sort_hist<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
     CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,

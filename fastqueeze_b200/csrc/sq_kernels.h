@@ -10,6 +10,8 @@
 #define SQ_TILE 8192            // sort tile: elements owned by one warp
 #define SQ_SORT_THREADS 256
 #define SQ_SORT_BITS 8          // radix digit width
+#define SQ_CHAIN_SMEM_RC (72 * 1024)      // dynamic shared memory requested only to cap chain CTAs per SM
+#define SQ_CHAIN_SMEM_SMALL (36 * 1024)
 
 // Everything the encode kernels of one wave need (all pointers are device pointers).
 struct EncWave {
@@ -44,7 +46,7 @@ cudaError_t sqk_count(const EncWave &w, cudaStream_t st, u64 *launches);
 cudaError_t sqk_emit(const EncWave &w, int stream, u64 *elem, cudaStream_t st, u64 *launches);
 cudaError_t sqk_sort(const EncWave &w, int stream, int keybits, u64 *a, u64 *b, u64 **sorted, cudaStream_t st, u64 *launches);
 cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *triples, cudaStream_t st, u64 *launches);
-cudaError_t sqk_rc(const EncWave &w, cudaStream_t st, u64 *launches);
+cudaError_t sqk_rc(const EncWave &w, int stream, cudaStream_t st, u64 *launches);
 cudaError_t sqk_md5(const EncWave &w, cudaStream_t st, u64 *launches);
 cudaError_t sqk_side(const EncWave &w, cudaStream_t st, u64 *launches);
 cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launches);

@@ -18,13 +18,15 @@ ap.add_argument("--pairs", type=int, default=73020)
 ap.add_argument("--kind", default="illumina_pe150")
 ap.add_argument("--decode", action="store_true")
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--ws-gb", type=float, default=0)
 a = ap.parse_args()
 
 blks = []
 for i in range(a.blocks):
-    d = sf.make_block(a.kind, n_templates=a.pairs, seed=100 + i, first=i * a.pairs)
-    blks.append(fq.SeqArcMemBuf(d["ids"], d["idlen"], d["seq"], d["qual"], d["seqlen"]))
-codec = fq.EncapFqzComp(fq.SeqArcParam(), workspace_bytes=(8 << 30) * max(1, a.blocks // 4 + 1))
+    if i < 4:
+        d = sf.make_block(a.kind, n_templates=a.pairs, seed=100 + i, first=i * a.pairs)
+    blks.append(fq.SeqArcMemBuf(d["ids"], d["idlen"], d["seq"], d["qual"], d["seqlen"]))   # blocks >= 4 repeat block 3 (timing only)
+codec = fq.EncapFqzComp(fq.SeqArcParam(), workspace_bytes=int(a.ws_gb * (1 << 30)) if a.ws_gb else int(1.3 * (1 << 30)) * a.blocks + (1 << 30))
 dbg = fq.DebugInfo()
 for _ in range(a.reps):
     t0 = time.time()
