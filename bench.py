@@ -256,7 +256,10 @@ def main():
 
     # ---- workload resident in HBM
     t0 = time.perf_counter()
-    blocks = [gen_block_device(torch, dev, rank * nblocks + i, PAIRS_PER_BLOCK, 7) for i in range(nblocks)]
+    # weak scaling: rank r owns blocks [r * nblocks, (r + 1) * nblocks) of an N-times larger job
+    from fastqueeze_b200.shard import block_range
+    lo, hi = block_range(nblocks * world, world, rank)
+    blocks = [gen_block_device(torch, dev, i, PAIRS_PER_BLOCK, 7) for i in range(lo, hi)]
     torch.cuda.synchronize()
     fastq_bytes = nblocks * 2 * PAIRS_PER_BLOCK * REC_BYTES
     in_bytes = sum(int(b["ids"].numel() + b["seq"].numel() + b["qual"].numel() + 6 * b["nreads"]) for b in blocks)
