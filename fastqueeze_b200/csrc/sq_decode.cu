@@ -21,7 +21,7 @@
 // the decoding warp, EPL consecutive entries per lane (lane l owns F[l*EPL .. l*EPL+EPL)):
 //   row i   (i < EPL), word l : entry i of lane l = sym | bub << 8 (row 0 only) | freq << 16
 //   row EPL,           word l : base_l | tot << 16, base_l = sum of the frequencies of all lower lanes
-//   row EPL+1,         word l : floor(2^32 / tot), so that range / tot is one multiply + one fix-up
+//   row EPL+1,         word l : reciprocal estimate of tot, so that range / tot is one multiply + fix-ups
 // Every word is only ever read and written by its own lane, every row is one coalesced 128-byte
 // access, and a symbol is found with EPL multiply-compares per lane + one ballot (no second division:
 // target = code / r  is replaced by comparing code with cum * r, which is the same test on integers).
@@ -40,10 +40,22 @@ SQ_D u32 warp_incl_scan_d(u32 v, int lane) {
     for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(FULL, v, o); if (lane >= o) v += t; }
     return v;
 }
-// floor(2^32 / tot), 2 <= tot <= 65535
-SQ_D u32 recip32(u32 tot) {
-    if ((tot & (tot - 1)) == 0) return 1u << (1 + __clz(tot));       // 2^32 / 2^k, k = 31 - clz
-    return 0xffffffffu / tot;
+// Reciprocal estimate e ~ 2^32 / d (never above it), the seed the compiler's own u32 division uses:
+// q' = mulhi(n, e) is within [floor(n / d) - 2, floor(n / d)] for every 32-bit n, so a division by
+// a divisor whose estimate is at hand is one multiply and at most two fix-up steps.
+SQ_D u32 recip_est(u32 d) {
+    float fr;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(fr) : "f"(__uint2float_ru(d)));
+    u32 e0 = __float2uint_rz(__uint_as_float(__float_as_uint(fr) + 0x0ffffffeu));
+    return e0 + __umulhi(e0, 0u - e0 * d);
+}
+SQ_D u32 div_est(u32 n, u32 d, u32 e) {
+    u32 q = __umulhi(n, e);
+    u32 r = n - q * d;
+    if (r >= d) { q++; r -= d; }
+    if (r >= d) { q++; r -= d; }
+    if (r >= d) q += r / d;              // never taken for a valid estimate; keeps the result exact regardless
+    return q;
 }
 
 // Range decoder with a byte window: the next bytes of the stream sit in a register and are
@@ -77,17 +89,31 @@ struct RcDecW {
         refill(); refill();
         for (int k = 0; k < 8; k++) code = (code << 8) | get();
     }
-    SQ_D void decode(u32 cum, u32 freq) {       // range already divided by tot
+    // range already divided by tot.  A symbol renormalises by at most two bytes (range / tot >= 2^8),
+    // so the common path shifts by 0 / 8 / 16 bits without a loop; the carry-less range adjustment
+    // (@0x429760-0x429880) needs bits 32..47 of low all ones, which sends us to the exact loop.
+    SQ_D void decode(u32 cum, u32 freq) {
         u32 t = cum * range;
         low += t;
         code -= t;
         range *= freq;
-        while (range < (1u << 24)) {
-            if ((low ^ (low + range)) >> 56) range = (((u32)low) | 0xffffffu) - (u32)low;
-            code = (code << 8) | get();
-            range <<= 8;
-            low <<= 8;
+        if (range >= (1u << 24)) return;
+        if ((~(u32)(low >> 32) & 0xffffu) == 0) {
+            while (range < (1u << 24)) {
+                if ((low ^ (low + range)) >> 56) range = (((u32)low) | 0xffffffu) - (u32)low;
+                code = (code << 8) | get();
+                range <<= 8;
+                low <<= 8;
+            }
+            return;
         }
+        u32 sh = range < (1u << 16) ? 16 : 8;
+        code = __funnelshift_l((u32)(win >> 32), code, sh);
+        win <<= sh;
+        avail -= (int)(sh >> 3);
+        range <<= sh;
+        low <<= sh;
+        if (avail <= 4) refill();
     }
 };
 
@@ -118,7 +144,7 @@ __global__ void __launch_bounds__(256) k_init_wm(DecBlock *db, int which, u32 nm
 #pragma unroll
         for (int i = 0; i < EPL; i++) mp[i * 32 + lane] = w[i];
         mp[EPL * 32 + lane] = base | (tot << 16);
-        mp[(EPL + 1) * 32 + lane] = recip32(tot < 2 ? 2 : tot);
+        mp[(EPL + 1) * 32 + lane] = recip_est(tot < 2 ? 2 : tot);
     }
 }
 __global__ void k_init_seqtab(DecBlock *db, u64 bytes, const u8 *snap) {
@@ -147,8 +173,7 @@ SQ_D void wm_load(WReg<EPL> &R, const u32 *mp, int lane) {
 template <int N, int EPL>
 SQ_D u32 wm_search(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li) {
     u32 base = R.bt & 0xffffu, tot = R.bt >> 16;
-    u32 q = __umulhi(rc.range, R.m32);
-    if (rc.range - q * tot >= tot) q++;
+    u32 q = div_est(rc.range, tot, R.m32);
     rc.range = q;
     u32 code = rc.code;
     li = -1;
@@ -161,11 +186,12 @@ SQ_D u32 wm_search(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li) {
         c = cn;
     }
     u32 bal = __ballot_sync(FULL, li >= 0);
-    if (bal) kl = __ffs(bal) - 1;
-    else {                                   // code beyond tot * r: corrupt stream; take the last symbol
-        kl = (N - 1) / EPL;
-        if (lane == kl) { li = (N - 1) % EPL; wsel = R.w[(N - 1) % EPL]; cex = c - (wsel >> 16); }
-    }
+    // code beyond tot * r only happens on a corrupt stream: take the last symbol then
+    bool lastl = (bal == 0) && (lane == (N - 1) / EPL);
+    li = lastl ? (N - 1) % EPL : li;
+    wsel = lastl ? R.w[(N - 1) % EPL] : wsel;
+    cex = lastl ? c - (R.w[(N - 1) % EPL] >> 16) : cex;
+    kl = bal ? (__ffs(bal) - 1) : (N - 1) / EPL;
     wsel = __shfl_sync(FULL, wsel, kl);
     cex = __shfl_sync(FULL, cex, kl);
     rc.decode(cex, wsel >> 16);
@@ -220,7 +246,7 @@ SQ_D void wm_update_store(u32 *mp, WReg<EPL> &R, int kl, int li, int lane) {
     }
     R.w[0] |= bub << 8;
     R.bt = base | (tot << 16);
-    R.m32 = recip32(tot);
+    R.m32 = recip_est(tot);
     // row 0 carries bub, the base row tot, the last row its reciprocal: rewritten by every lane
     mp[lane] = R.w[0];
     mp[EPL * 32 + lane] = R.bt;
@@ -332,7 +358,7 @@ struct SeqPipe {
     SQ_D void init() { step = 0; lc0 = lc1 = lc2 = lc3 = 0xffffffffu; lv0 = lv1 = lv2 = lv3 = 0; }
 };
 
-SQ_D u32 decode_base(u8 *seqtab, u32 *ring, RcDecW &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane) {
+SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane) {
     {
         u32 base4 = (last << 8) & mask;
         const u8 *src = seqtab + ((u64)base4 << 2) + lane * 32;
@@ -357,16 +383,17 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, RcDecW &rc, u32 &last, u32 mask, u32
     u32 S0 = x & 0xff, S1 = (x >> 8) & 0xff, S2 = (x >> 16) & 0xff, S3 = x >> 24;
     u32 tot = S0 + S1 + S2 + S3;
     if (tot > 253) { S0 -= S0 >> 1; S1 -= S1 >> 1; S2 -= S2 >> 1; S3 -= S3 >> 1; tot = S0 + S1 + S2 + S3; }
-    rc.range /= tot;
-    u32 r = rc.range, code = rc.code;
-    u32 b, cum, f;
-    if (code < S0 * r) { b = 0; cum = 0; f = S0; }
-    else if (code < (S0 + S1) * r) { b = 1; cum = S0; f = S1; }
-    else if (code < (S0 + S1 + S2) * r) { b = 2; cum = S0 + S1; f = S2; }
-    else { b = 3; cum = S0 + S1 + S2; f = S3; }
+    u32 r = div_est(rc.range, tot, rlut[tot]);
+    rc.range = r;
+    u32 code = rc.code;
+    u32 c1 = S0, c2 = S0 + S1, c3 = c2 + S2;
+    u32 b = (u32)(code >= c1 * r) + (u32)(code >= c2 * r) + (u32)(code >= c3 * r);
+    u32 cum = b == 0 ? 0u : (b == 1 ? c1 : (b == 2 ? c2 : c3));
+    u32 f = b == 0 ? S0 : (b == 1 ? S1 : (b == 2 ? S2 : S3));
     rc.decode(cum, f);
-    if (b == 0) S0 = (S0 + 1) & 0xff; else if (b == 1) S1 = (S1 + 1) & 0xff; else if (b == 2) S2 = (S2 + 1) & 0xff; else S3 = (S3 + 1) & 0xff;
-    u32 nv = S0 | (S1 << 8) | (S2 << 16) | (S3 << 24);
+    u32 packed = S0 | (S1 << 8) | (S2 << 16) | (S3 << 24);
+    u32 inc = 1u << (8 * b);
+    u32 nv = (f == 255) ? (packed & ~(0xffu << (8 * b))) : packed + inc;     // (S[b] + 1) & 0xff
     *S4 = nv;
     __syncwarp();
     P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
@@ -407,6 +434,7 @@ struct KModelD {
 };
 struct MainSmem {
     u32 ring[8 * 256];         // base-model candidate ring of the seq warp
+    u32 rlut[1024];            // reciprocal estimates of every possible base-model total (<= 1020)
     NameSmem ns;
     SmModel<2> tip;
     SmModel<11> ch;
@@ -417,11 +445,14 @@ struct MainSmem {
     volatile u32 qprog;        // reads whose qualities are complete
 };
 
-__global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int qlevel, int id_rule, u32 seqmask) {
+template <int QLEVEL>
+__global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 seqmask) {
+    constexpr int qlevel = QLEVEL;
     __shared__ __align__(16) MainSmem sm;
     DecBlock &d = db[blockIdx.x];
     int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { sm.qprog = 0; sm.side_err = 0; }
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm.rlut[i] = recip_est(i < 2 ? 2 : i);
     __syncthreads();
     if (d.status != 0) return;
     const char tbl[] = "ACGT";
@@ -540,7 +571,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int qlevel, int i
             bool flagged = r < n_tip && __ldcg(d_tip + r);
             if (!flagged) {
                 for (int i = 0; i < len; i++) {
-                    u32 bb = decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane);
+                    u32 bb = decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane);
                     if (lane == 0) seq[i] = (u8)tbl[bb];
                 }
                 continue;
@@ -556,7 +587,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int qlevel, int i
                 for (int i = 0; i < len; i++) {
                     u32 c;
                     if (mq >= (int)(int8_t)__ldcg(qual + i)) { c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
-                    else c = (u8)tbl[decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane)];
+                    else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane)];
                     if (lane == 0) seq[i] = (u8)c;
                 }
                 continue;
@@ -569,10 +600,10 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int qlevel, int i
                     if (run == gap) {                          // @0x429b40
                         gap = 0xffffffffu;
                         if (remaining) { remaining--; gap = i_pos < n_pos ? __ldcg(d_pos + i_pos) : 0; i_pos++; }
-                        c = (u8)tbl[decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane)];
+                        c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane)];
                         run = 0;
                     } else { run++; c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
-                } else c = (u8)tbl[decode_base(seqtab, sm.ring, rc, last, seqmask, nb++, P, lane)];
+                } else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane)];
                 if (lane == 0) seq[i] = (u8)c;
             }
         }
@@ -614,7 +645,9 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
         *launches += 2;
     }
     k_dec_len<<<B, 32, 0, st>>>(w.db);
-    k_dec_main<<<B, 96, 0, st>>>(w.db, w.qlevel, w.id_rule, w.seqmask);
+    if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
+    else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
+    else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
     *launches += 2;
     if (w.md5) { k_dec_md5<<<cdivd(3ull * B, 32), 32, 0, st>>>(w.db, B); *launches += 1; }
     return cudaGetLastError();

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "SeqArc-1.6")
 NLGUARD = os.path.join(HERE, "_ref", "nlguard.so")
+SIZEFAKE = os.path.join(HERE, "_ref", "sizefake.so")
 
 
 class Params(C.Structure):
@@ -140,6 +141,17 @@ class Oracle:
         n = lib().sqo_trace_stream(self.h, C.byref(cb), which, tr.ctypes.data, scratch.ctypes.data)
         return tr[:n].copy()
 
+    def train(self, blocks) -> bytes:
+        """encodeForModel @0x4228e0 over the sample blocks (no reset in between) + SaveModelToMem @0x420c00."""
+        for j, blk in enumerate(blocks):
+            cb = blk.cblock()
+            lib().sqo_train_block(self.h, C.byref(cb), 1 if j == 0 else 0)
+        n = int(lib().sqo_model_size(C.byref(self.p)))
+        buf = np.zeros(n, np.uint8)
+        got = lib().sqo_save_model(self.h, buf.ctypes.data)
+        assert got == n
+        return buf.tobytes()
+
     def decode_block(self, rec: bytes, idcap=None, seqcap=None, readcap=None) -> Block:
         rec_a = np.frombuffer(rec, dtype=np.uint8)
         seqcap = seqcap or (64 << 20)
@@ -226,11 +238,14 @@ def have_ref():
     return os.path.exists(REF_BIN)
 
 
-def run_ref(args, cwd, lossy_shim=False, config=None, timeout=3600):
+def run_ref(args, cwd, lossy_shim=False, config=None, timeout=3600, fake_size=None):
     """Run the unmodified reference executable in `cwd` (it reads ./seqarc.config from there)."""
     env = dict(os.environ)
     if lossy_shim:
         env["LD_PRELOAD"] = NLGUARD
+    if fake_size:      # make the reference take its usemodel = 1 path on a small input (oracle/sizefake.c)
+        env["LD_PRELOAD"] = SIZEFAKE
+        env["SQ_FAKE_SIZE"] = str(int(fake_size))
     cfg = os.path.join(cwd, "seqarc.config")
     if config:
         with open(cfg, "w") as f:

@@ -26,14 +26,67 @@ def case_fastq(name):
     return t if m["pe"] else (t,)
 
 
+def preprocess_sample(fastq: bytes, blocksize: int, max_blocks: int = 5):
+    """The reads SeqArcPreProcess::doPreProcess @0x4153b0 trains the model snapshot on (SE): up to five head
+    blocks, each taking whole records until it holds at least `blocksize` bytes (measured against the
+    reference: 5 x 4298 reads of 244 B at BlockSize 1 MiB, one more read per block than the encoder's blocks)."""
+    recs = po.parse_fastq(fastq)
+    out, i = [], 0
+    for _ in range(max_blocks):
+        if i >= len(recs):
+            break
+        size, j = 0, i
+        while j < len(recs) and size < blocksize:
+            size += len(recs[j][0]) + len(recs[j][1]) + len(recs[j][2]) + 6
+            j += 1
+        out.append(po.block_from_records(recs[i:j]))
+        i = j
+    return out
+
+
+_MODEL_CACHE = {}
+
+
+def case_model(name):
+    """Model snapshot of a usemodel golden case, rebuilt by the oracle's training twins and checked against
+    the md5 of the blob the reference wrote (the 27 MB blob itself is not committed)."""
+    import hashlib
+    if name not in _MODEL_CACHE:
+        m = MANIFEST[name]
+        bs = int((m["config"] or {}).get("BlockSize(M)", 50)) << 20
+        fq = case_fastq(name)
+        assert not m["pe"]
+        o = po.Oracle(usemodel=0, id_rule=0)
+        blob = o.train(preprocess_sample(fq[0], bs))
+        assert hashlib.md5(blob).hexdigest() == m["model_md5"], "oracle-trained snapshot differs from the reference's"
+        _MODEL_CACHE[name] = blob
+    return _MODEL_CACHE[name]
+
+
+def case_archive(name):
+    m = MANIFEST[name]
+    if not m.get("usemodel"):
+        return open(os.path.join(GOLD, name + ".arc"), "rb").read()
+    stripped = open(os.path.join(GOLD, name + ".arc_nomodel"), "rb").read()
+    blob = bytes([0x81, 0x82, 0x01, 0x00]) + case_model(name)
+    n = len(blob) | (1 << 28)
+    cut = m["model_cut"]
+    return stripped[:cut] + bytes([0x86]) + n.to_bytes(4, "big") + blob + stripped[cut:]
+
+
 def case_params(name):
     """Coder options of a golden case as kwargs of pyoracle.Oracle / fastqueeze_b200.SeqArcParam."""
+    import hashlib
     m = MANIFEST[name]
-    arc = arcwalk.parse_arc(open(os.path.join(GOLD, name + ".arc"), "rb").read())
+    data = case_archive(name)
+    assert hashlib.md5(data).hexdigest() == m["arc_md5"]
+    arc = arcwalk.parse_arc(data)
     cfg = m["config"] or {}
     idbin = arc["trailer"]["params"][15]
-    kw = dict(usemodel=0, lossy=0, lossy_r=0.0, md5=0 if "-n" in m["opts"] else 1,
+    kw = dict(usemodel=int(m.get("usemodel", 0)), lossy=0, lossy_r=0.0, md5=0 if "-n" in m["opts"] else 1,
               slevel=int(cfg.get("Slevel", 3)), qlevel=int(cfg.get("Qlevel", 2)), id_rule=int(idbin[0]))
+    if kw["usemodel"]:
+        kw["model"] = arc["trailer"]["model"][4:]
     if "-l" in m["opts"]:
         kw["lossy"] = 1
         kw["lossy_r"] = float(m["opts"][m["opts"].index("-l") + 1])
@@ -69,7 +122,8 @@ def to_membuf(blk):
 def to_param(kw, model=None):
     from fastqueeze_b200 import SeqArcParam
     return SeqArcParam(usemodel=kw["usemodel"], lossy=kw["lossy"], lossy_r=kw["lossy_r"], md5=kw["md5"],
-                       Slevel=kw["slevel"], Qlevel=kw["qlevel"], id_rule=kw["id_rule"], modelbuf=model)
+                       Slevel=kw["slevel"], Qlevel=kw["qlevel"], id_rule=kw["id_rule"],
+                       modelbuf=model if model is not None else kw.get("model"))
 
 
 def synth_block(**kw):

@@ -37,6 +37,10 @@ CASES = [
     dict(name="srr_pe100", src=dict(kind="srr_pe100", n_templates=1200, seed=3), pe=True, opts=[], config=None),
     dict(name="illumina_pe150_q1", src=dict(kind="illumina_pe150", n_templates=800, seed=21, hash_tail=0.1), pe=True, opts=[],
          config={"Qlevel": 1}),
+    # usemodel = 1 (snapshot trained on the head blocks): forced by the size-faking shim, archive too big to commit
+    # (27 MB model blob) -> only the block records, the block index and the md5 of the model blob are kept
+    dict(name="se100_q8_usemodel", src=dict(kind="se100_q8", n_templates=14000, seed=77), pe=False, opts=[],
+         config={"BlockSize(M)": 1}, fake_size=15000000000),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
@@ -79,14 +83,28 @@ def main():
             else:
                 args += ["-1", names[0]]
             args += ["-o", "out"]
-            rc, log = po.run_ref(args, tmp, lossy_shim=case.get("shim", False), config=case["config"])
+            rc, log = po.run_ref(args, tmp, lossy_shim=case.get("shim", False), config=case["config"],
+                                 fake_size=case.get("fake_size"))
             assert rc == 0, (case["name"], rc, log[-2000:])
             arc = open(os.path.join(tmp, "out.arc"), "rb").read()
-            open(os.path.join(GOLD, case["name"] + ".arc"), "wb").write(arc)
-            manifest[case["name"]] = dict(src=case["src"], pe=case["pe"], opts=case["opts"], config=case["config"],
-                                          shim=case.get("shim", False), arc_bytes=len(arc),
-                                          arc_md5=hashlib.md5(arc).hexdigest(),
-                                          fastq_md5=[hashlib.md5(t).hexdigest() for t in fq])
+            entry = dict(src=case["src"], pe=case["pe"], opts=case["opts"], config=case["config"],
+                         shim=case.get("shim", False), arc_bytes=len(arc), arc_md5=hashlib.md5(arc).hexdigest(),
+                         fastq_md5=[hashlib.md5(t).hexdigest() for t in fq])
+            if case.get("fake_size"):
+                from oracle import arcwalk
+                assert "usemodel=1" in log, log[-1500:]
+                pa = arcwalk.parse_arc(arc)
+                model = pa["trailer"]["model"]
+                assert model[:4] == bytes([0x81, 0x82, 0x01, 0x00])
+                # stripped archive: everything except the model blob (header + blocks | trailer without tag 6)
+                cut0 = arc.index(model[:64]) - 5          # tag 6 + size(4) precede the payload
+                stripped = arc[:cut0] + arc[cut0 + 5 + len(model):]
+                open(os.path.join(GOLD, case["name"] + ".arc_nomodel"), "wb").write(stripped)
+                entry.update(usemodel=1, model_bytes=len(model) - 4, model_md5=hashlib.md5(model[4:]).hexdigest(),
+                             model_cut=cut0, fake_size=case["fake_size"])
+            else:
+                open(os.path.join(GOLD, case["name"] + ".arc"), "wb").write(arc)
+            manifest[case["name"]] = entry
             print(case["name"], len(arc), "bytes")
         finally:
             shutil.rmtree(tmp)
