@@ -16,7 +16,7 @@ STATUS = {0: "SQ_OK", -1: "SQ_ERR_NO_DEVICE", -2: "SQ_ERR_CUDA", -3: "SQ_ERR_ARG
           -9: "SQ_ERR_MD5_SEQ", -10: "SQ_ERR_MD5_QUAL"}
 
 # every symbol include/seqarc_b200.h declares
-EXPORTS = ["sq_create", "sq_destroy", "sq_last_error", "sq_load_model", "sq_model_size", "sq_encode_blocks",
+EXPORTS = ["sq_create", "sq_destroy", "sq_last_error", "sq_load_model", "sq_model_size", "sq_train_model", "sq_encode_blocks",
            "sq_encode_blocks_dev", "sq_decode_blocks", "sq_decode_blocks_dev", "sq_rblock", "sq_last_timings",
            "sq_last_launches", "sq_last_wave_blocks", "sq_debug_fetch", "sq_version"]
 
@@ -79,6 +79,8 @@ def lib():
         f = getattr(L, n)
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int, C.POINTER(SqBlockDec)]
+    L.sq_train_model.restype = C.c_int
+    L.sq_train_model.argtypes = [C.c_void_p, C.POINTER(SqBlockIn), C.c_int, C.c_void_p, C.c_uint64]
     L.sq_rblock.restype = C.c_int
     L.sq_rblock.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double]
     L.sq_last_timings.restype = C.c_int

@@ -104,6 +104,25 @@ class EncapFqzComp:
     def model_size(self):
         return int(self._L.sq_model_size(self._h))
 
+    # encodeForModel @0x4228e0 + SaveModelToMem @0x420c00: train the snapshot on the sample blocks
+    def encodeForModel(self, membufs) -> bytes:
+        n = len(membufs)
+        ins = (SqBlockIn * n)()
+        keep = []
+        for i, m in enumerate(membufs):
+            ids, seq, qual = _c(m.ids, np.uint8), _c(m.seq, np.uint8), _c(m.qual, np.uint8)
+            idlen, seqlen = _c(m.idlen, np.uint16), _c(m.seqlen, np.int32)
+            keep.append((ids, seq, qual, idlen, seqlen))
+            ins[i].nreads = seqlen.shape[0]
+            ins[i].ids, ins[i].seq, ins[i].qual = ids.ctypes.data, seq.ctypes.data, qual.ctypes.data
+            ins[i].idlen, ins[i].seqlen = idlen.ctypes.data, seqlen.ctypes.data
+            ins[i].idbytes, ins[i].seqbytes = ids.shape[0], seq.shape[0]
+        blob = np.empty(self.model_size(), np.uint8)
+        r = self._L.sq_train_model(self._h, ins, n, blob.ctypes.data, blob.shape[0])
+        if r != 0:
+            raise self._err(r)
+        return blob.tobytes()
+
     def _debug(self, dbg):
         if dbg is None:
             return

@@ -247,7 +247,7 @@ struct WaveAcc {
 
 template <class T> T *take(Arena &a, u64 count) { return (T *)a.take(count * sizeof(T)); }
 
-int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, bool host) {
+int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, bool host, u8 *train_blob = nullptr) {
     cudaStream_t st = c->stream;
     Arena &A = c->arena;
     A.reset();
@@ -255,7 +255,11 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     w.B = n; w.nsm = c->nsm;
     w.md5 = c->p.md5; w.lossy = c->p.lossy; w.id_rule = c->p.id_rule; w.qlevel = c->p.qlevel;
     w.seqmask = c->nseq() - 1;
-    if (c->p.usemodel) {
+    if (train_blob) {            // encodeForModel @0x4228e0: models start from the constructor state
+        w.train_name = c->p.id_rule ? nullptr : train_blob;
+        w.train_seq = train_blob + c->snap_name_bytes();
+        w.train_qual = w.train_seq + (u64)c->nseq() * 4;
+    } else if (c->p.usemodel) {
         if (!c->d_model) { c->err = "usemodel = 1 but no snapshot loaded (sq_load_model)"; return SQ_ERR_ARG; }
         w.snap_name = c->p.id_rule ? nullptr : c->d_model;
         w.snap_seq = c->d_model + c->snap_name_bytes();
@@ -387,6 +391,25 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     T.close(sp, s_side);
     CUDA_OK(c, cudaEventRecord(c->ev[3], s_side));
 
+    if (train_blob) {
+        // the md5 / side kernels launched above are harmless here; only the model replays matter
+        int kb[3] = {(int)(2 * c->NS()), c->p.qlevel > 2 ? 20 : 16, 14};
+        for (int s = 0; s < ST_COUNT; s++) {
+            if (s == ST_NAME && c->p.id_rule) continue;
+            u64 *sorted = nullptr;
+            CUDA_OK(c, sqk_emit(w, s, w.elemA, st, L));
+            CUDA_OK(c, sqk_sort(w, s, kb[s], w.elemA, w.elemB, &sorted, st, L));
+            CUDA_OK(c, sqk_replay(w, s, sorted, w.triples[s], st, L));
+        }
+        CUDA_OK(c, cudaStreamWaitEvent(st, c->ev[1], 0));
+        CUDA_OK(c, cudaStreamWaitEvent(st, c->ev[3], 0));
+        BlockState hb;
+        CUDA_OK(c, cudaMemcpyAsync(&hb, w.bs, sizeof hb, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(c, cudaStreamSynchronize(st));
+        T.collect();
+        if (hb.status) { c->err = "training input rejected"; return hb.status; }
+        return SQ_OK;
+    }
     static const char *nm_emit[3] = {"seq.ctx", "qual.ctx", "name.ctx"};
     static const char *nm_sort[3] = {"seq.sort", "qual.sort", "name.sort"};
     static const char *nm_rep[3] = {"seq.replay", "qual.replay", "name.replay"};
@@ -490,6 +513,67 @@ extern "C" int sq_encode_blocks(sq_ctx *c, const sq_block_in *blocks, int n, sq_
 }
 extern "C" int sq_encode_blocks_dev(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out) {
     return encode_blocks(c, blocks, n, out, false);
+}
+
+// SeqArcPreProcess::doPreProcess @0x4153b0 -> EncapFqzComp::encodeForModel @0x4228e0 (the *_formodel twins
+// update the models without coding and without a reset between the sample blocks) -> SaveModelToMem
+// @0x420c00.  The sample blocks are laid end to end as ONE block and pushed through the same context /
+// sort / replay kernels as an encode; the replay kernels write each model's final state instead of triples.
+extern "C" int sq_train_model(sq_ctx *c, const sq_block_in *blocks, int n, uint8_t *blob, uint64_t cap) {
+    if (!c || !blocks || n <= 0 || !blob) { if (c) c->err = "bad argument"; return SQ_ERR_ARG; }
+    u64 msize = sq_model_size(c);
+    if (cap < msize) { c->err = "model buffer too small"; return SQ_ERR_CAPACITY; }
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    u64 nr = 0, ib = 0, sb = 0;
+    for (int i = 0; i < n; i++) { nr += blocks[i].nreads; ib += blocks[i].idbytes; sb += blocks[i].seqbytes; }
+    if (nr >= (1ull << 31) || sb >= (1ull << 31) || ib >= (1ull << 31)) { c->err = "training sample too large"; return SQ_ERR_ARG; }
+    // merged device copy (outside the arena: the arena is carved by encode_wave)
+    u8 *d = nullptr;
+    u64 o_ids = 0, o_seq = al16(ib) + 16, o_qual = o_seq + al16(sb) + 16, o_il = o_qual + al16(sb) + 16,
+        o_sl = o_il + al16(2 * nr) + 16, o_blob = o_sl + al16(4 * nr) + 16, tot = o_blob + msize + 16;
+    CUDA_OK(c, cudaMalloc((void **)&d, tot));
+    cudaStream_t st = c->stream;
+    u64 a = 0, b = 0, r = 0;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n && e == cudaSuccess; i++) {
+        const sq_block_in &k = blocks[i];
+        if (k.idbytes) e = cudaMemcpyAsync(d + o_ids + a, k.ids, k.idbytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && k.seqbytes) e = cudaMemcpyAsync(d + o_seq + b, k.seq, k.seqbytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && k.seqbytes) e = cudaMemcpyAsync(d + o_qual + b, k.qual, k.seqbytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && k.nreads) e = cudaMemcpyAsync(d + o_il + 2 * r, k.idlen, 2ull * k.nreads, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && k.nreads) e = cudaMemcpyAsync(d + o_sl + 4 * r, k.seqlen, 4ull * k.nreads, cudaMemcpyHostToDevice, st);
+        a += k.idbytes; b += k.seqbytes; r += k.nreads;
+    }
+    int rc = SQ_OK;
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = SQ_ERR_CUDA; }
+    if (rc == SQ_OK) {
+        u64 l = 0;
+        e = sqk_snap_init(d + o_blob, c->snap_name_bytes(), c->nseq(), c->nqual(), st, &l);
+        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = SQ_ERR_CUDA; }
+    }
+    if (rc == SQ_OK) {
+        sq_block_in m{};
+        m.nreads = (u32)nr; m.ids = d + o_ids; m.seq = d + o_seq; m.qual = d + o_qual;
+        m.idlen = (const u16 *)(d + o_il); m.seqlen = (const i32 *)(d + o_sl);
+        m.idbytes = ib; m.seqbytes = sb;
+        sq_block_out dummy{};
+        sq_params keep = c->p;
+        c->p.lossy = 0;                                     // the snapshot is trained on the original qualities
+        c->timer.acc.clear();
+        c->launches = 0;
+        WaveAcc acc;
+        acc.add(c, block_cost(c, m, false));
+        if (acc.total(c) > c->arena.cap) { c->err = "training sample does not fit the device workspace"; rc = SQ_ERR_NOMEM; }
+        else rc = encode_wave(c, &m, 1, &dummy, false, d + o_blob);
+        c->p = keep;
+        c->last_valid = false;
+    }
+    if (rc == SQ_OK) {
+        e = cudaMemcpy(blob, d + o_blob, msize, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = SQ_ERR_CUDA; }
+    }
+    cudaFree(d);
+    return rc;
 }
 
 extern "C" int sq_debug_fetch(sq_ctx *c, int what, int block, void *dst, uint64_t cap, uint64_t *got) {

@@ -410,7 +410,7 @@ SQ_D u32 grab32(u32 *cursor, int lane) {
 // next element is fetched one step ahead and the line after next is prefetched into L1.
 __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockDesc *bd, const BlockState *bs,
                                                     const u64 *seglist, const u32 *nseg, u32 *cursor,
-                                                    u64 *triples, const u8 *snap_seq) {
+                                                    u64 *triples, const u8 *snap_seq, u8 *train_out) {
     int lane = threadIdx.x & 31;
     u32 total = *nseg;
     for (;;) {
@@ -443,13 +443,17 @@ __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockD
             else if (sym == 1) { cum = S0; f = S1; S1 = (S1 + 1) & 0xff; }
             else if (sym == 2) { cum = S0 + S1; f = S2; S2 = (S2 + 1) & 0xff; }
             else { cum = S0 + S1 + S2; f = S3; S3 = (S3 + 1) & 0xff; }
-            out[el_pos(e)] = tr_make(cum, f, tot);
+            if (!train_out) out[el_pos(e)] = tr_make(cum, f, tot);
             if (!hn) break;
             e = en;
             g++;
             if (el_key(e) != key) break;
             hn = g + 1 < end;
             if (hn) en = src[g + 1];
+        }
+        if (train_out) {          // encode_seq_formodel @0x4220c0: the counters after the last sampled base
+            u8 *t = train_out + (u64)key * 4;
+            t[0] = (u8)S0; t[1] = (u8)S1; t[2] = (u8)S2; t[3] = (u8)S3;
         }
     }
 }
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockD
 template <int N, int EPL>
 __global__ void __launch_bounds__(128) k_replay_warp(const u64 *src, const BlockDesc *bd, const BlockState *bs, int stream,
                                                      const u64 *seglist, const u32 *nseg, u32 *cursor, u64 *triples,
-                                                     u32 keylo, u32 keyhi, const u8 *snap, u32 snapstride) {
+                                                     u32 keylo, u32 keyhi, const u8 *snap, u32 snapstride, u8 *train_out) {
     static_assert(EPL * 32 >= N, "lanes must cover the model");
     int lane = threadIdx.x & 31;
     u32 total = *nseg;
@@ -568,12 +572,42 @@ __global__ void __launch_bounds__(128) k_replay_warp(const u64 *src, const Block
                     }
                 }
             }
-            if (lane < cnt) out[el_pos(e)] = mytr;
+            if (lane < cnt && !train_out) out[el_pos(e)] = mytr;
             if (cnt < 32) break;
             gi = gn;
             e = en;
             if (gi - lane >= end) break;
         }
+        if (train_out) {          // SaveModelToMem @0x420c00: u32le Tot, u32le Bub, N x {u8 sym, u16le freq} in table order
+            u8 *t = train_out + (u64)(key - keylo) * snapstride;
+            if (lane == 0) { put_u32le(t, tot); put_u32le(t + 4, bub); }
+#pragma unroll
+            for (int i = 0; i < EPL; i++) {
+                int slot = lane * EPL + i;
+                if (slot < N) { u8 *q = t + 8 + 3 * slot; q[0] = (u8)sy[i]; q[1] = (u8)fr[i]; q[2] = (u8)(fr[i] >> 8); }
+            }
+        }
+    }
+}
+
+// default (constructor-state) snapshot: what SaveModelToMem would write for untouched models
+__global__ void k_snap_init(u8 *blob, u64 name_bytes, u32 nseq, u32 nqual) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 nname = name_bytes ? 768 + 8192 : 0;
+    u64 total = nname + nseq + nqual;
+    if (i >= total) return;
+    if (i < nname) {
+        int N = i < 768 ? 256 : 128;
+        u8 *t = blob + (i < 768 ? i * 776 : 768ull * 776 + (i - 768) * 392);
+        put_u32le(t, (u32)N); put_u32le(t + 4, 0);
+        for (int k = 0; k < N; k++) { t[8 + 3 * k] = (u8)k; t[9 + 3 * k] = 1; t[10 + 3 * k] = 0; }
+    } else if (i < nname + nseq) {
+        u8 *t = blob + name_bytes + (i - nname) * 4;
+        t[0] = t[1] = t[2] = t[3] = 3;
+    } else {
+        u8 *t = blob + name_bytes + (u64)nseq * 4 + (i - nname - nseq) * 293;
+        put_u32le(t, 95); put_u32le(t + 4, 0);
+        for (int k = 0; k < 95; k++) { t[8 + 3 * k] = (u8)k; t[9 + 3 * k] = 1; t[10 + 3 * k] = 0; }
     }
 }
 
@@ -1098,20 +1132,28 @@ cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *tri
     *launches += 1;
     int nsm = w.nsm;
     if (stream == ST_SEQ) {
-        k_replay_seq<<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, triples, w.snap_seq);
+        k_replay_seq<<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, triples, w.snap_seq, w.train_seq);
         *launches += 1;
     } else if (stream == ST_QUAL) {
         k_replay_warp<95, 3><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1, triples,
-                                                    0, 1u << 24, w.snap_qual, 293);
+                                                    0, 1u << 24, w.snap_qual, 293, w.train_qual);
         *launches += 1;
     } else {
         k_replay_warp<256, 8><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1,
-                                                     triples, 0, NK_MIDDLE, w.snap_name, 776);
+                                                     triples, 0, NK_MIDDLE, w.snap_name, 776, w.train_name);
         k_replay_warp<128, 4><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 2,
                                                      triples, NK_MIDDLE, NK_TOTAL,
-                                                     w.snap_name ? w.snap_name + 3ull * 256 * 776 : nullptr, 392);
+                                                     w.snap_name ? w.snap_name + 3ull * 256 * 776 : nullptr, 392,
+                                                     w.train_name ? w.train_name + 3ull * 256 * 776 : nullptr);
         *launches += 2;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t sqk_snap_init(u8 *blob, u64 name_bytes, u32 nseq, u32 nqual, cudaStream_t st, u64 *launches) {
+    u64 total = (name_bytes ? 768 + 8192 : 0) + (u64)nseq + nqual;
+    k_snap_init<<<cdiv(total, 256), 256, 0, st>>>(blob, name_bytes, nseq, nqual);
+    *launches += 1;
     return cudaGetLastError();
 }
 

@@ -37,6 +37,7 @@ struct EncWave {
     u8 *sidebuf;
     u8 *recbuf; u64 recbuf_cap; u64 *recoff;   // compact record buffer, [B+1] offsets
     const u8 *snap_name, *snap_seq, *snap_qual;   // model snapshot sections (usemodel) or null
+    u8 *train_name, *train_seq, *train_qual;      // training (encodeForModel): where the final model states go, or null
 };
 
 cudaError_t sqk_enc_attrs();
@@ -49,6 +50,7 @@ cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *tri
 cudaError_t sqk_rc(const EncWave &w, int stream, cudaStream_t st, u64 *launches);
 cudaError_t sqk_md5(const EncWave &w, cudaStream_t st, u64 *launches);
 cudaError_t sqk_side(const EncWave &w, cudaStream_t st, u64 *launches);
+cudaError_t sqk_snap_init(u8 *blob, u64 name_bytes, u32 nseq, u32 nqual, cudaStream_t st, u64 *launches);
 cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launches);
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,53 @@
+// arc_file.h -- the .arc container, format version 1.6, writer and reader.
+//   SeqArcFile::SeqArcFile     @0x415c20  ".arc" 01 06 00, TAG 2 with an 8-byte size patched at the end
+//   SeqArcFile::writeFileInfo  @0x4171b0  trailer: TAG 3 { TAG 1 params | [TAG 6 model] | TAG 7 block index }
+//   SeqArcFile::writeParam     @0x416450  params 1..18
+//   SeqArcFile::readFileInfo   @0x419660
+//   Encap::setID / setSize / getValue @0x420680-0x4207bd  (EBML-style vints)
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sqhost {
+
+struct ArcParams {
+    bool pe = false;               // param 3 is 1 for single-end input
+    bool usemodel = false;         // param 6
+    bool lossy = false;            // param 16
+    bool md5 = true;               // param 17
+    std::string name1, name2;      // params 13 / 14: base names of the inputs
+    uint8_t idbin[512] = {0};      // param 15: ID-bin types (idbin[0] = 1: rule-based ID path)
+    std::vector<uint8_t> model;    // trailer TAG 6 payload after its "TAG 1, u16 = 1" header
+};
+
+struct BlockIndex {                // one record of trailer TAG 7 (32 B single-end, 40 B paired-end)
+    uint32_t len = 0;              // bytes of the block record
+    uint32_t src_bytes[2] = {0, 0};
+    uint64_t arc_off = 0;          // offset of the record in the .arc (first one: 16)
+    uint64_t src_off[2] = {0, 0};
+};
+
+class ArcWriter {
+public:
+    bool open(const std::string &path);
+    // append one block record (already "tag 1 | size(4) | streams"); records must come in block order
+    void add_block(const uint8_t *rec, uint64_t len, const uint64_t src_bytes[2], const uint64_t src_off[2]);
+    bool finish(const ArcParams &p);
+    uint64_t bytes() const { return off_; }
+
+private:
+    FILE *f_ = nullptr;
+    uint64_t off_ = 0;
+    std::vector<BlockIndex> idx_;
+};
+
+struct ArcReader {
+    ArcParams p;
+    std::vector<BlockIndex> idx;
+    std::vector<uint8_t> data;     // whole file
+    std::string err;
+    bool load(const std::string &path);
+};
+
+}  // namespace sqhost

@@ -1,0 +1,162 @@
+#include "fastq_block.h"
+
+#include <cstring>
+#include <stdexcept>
+
+namespace sqhost {
+
+BlockReader::BlockReader(const std::string &p1, const std::string &p2, uint64_t block_bytes) : block_bytes_(block_bytes) {
+    pe_ = !p2.empty();
+    f_[0] = fopen(p1.c_str(), "rb");
+    if (pe_) f_[1] = fopen(p2.c_str(), "rb");
+}
+BlockReader::~BlockReader() {
+    for (auto f : f_) if (f) fclose(f);
+}
+
+// getEndPos @0x4320c0: scan backwards from index `len` for buf[p] == '\n' && buf[p+1] == '@' such that
+// buf[p+1+k] == firstline[k] holds for 6 CONSECUTIVE k somewhere in [0, |firstline|).  Bytes at or
+// beyond `valid` are stale memory in the reference; they are treated as non-matching here.
+int BlockReader::get_end_pos(int len, const char *buf, int valid, const std::string &first) {
+    for (int p = len; p > 0; p--) {
+        if (buf[p] != '\n' || p + 1 >= valid || buf[p + 1] != '@') continue;
+        int run = 0;
+        for (size_t k = 0; k < first.size(); k++) {
+            int q = p + 1 + (int)k;
+            if (q < valid && buf[q] == first[k]) { if (++run > 5) return p; }
+            else run = 0;
+        }
+    }
+    return 0;
+}
+
+static void first_line(const char *buf, size_t n, std::string &out) {     // getFirstLine @0x431eb0
+    size_t i = 0;
+    while (i < n && buf[i] != '\n') i++;
+    out.assign(buf, i < n ? i + 1 : n);
+}
+
+bool BlockReader::next_text(std::vector<char> &t1, std::vector<char> &t2) {
+    t1.clear(); t2.clear();
+    if (eof_) return false;
+    const int nf = pe_ ? 2 : 1;
+    uint64_t quota = pe_ ? block_bytes_ / 2 : block_bytes_;            // @0x432dd2: shr $1 for PE
+    std::vector<char> *t[2] = {&t1, &t2};
+    bool shortread = false;
+    for (int k = 0; k < nf; k++) {
+        std::vector<char> &b = *t[k];
+        size_t L = left_[k].size();
+        b.resize(quota + 1);
+        memcpy(b.data(), left_[k].data(), L);
+        left_[k].clear();
+        size_t want = quota > L ? quota - L : 0;
+        size_t got = want ? fread(b.data() + L, 1, want, f_[k]) : 0;
+        if (first_[k].empty()) first_line(b.data() + L, got, first_[k]);
+        if (got < want) shortread = true;
+        b.resize(L + got);
+    }
+    if (shortread) {                      // end of input: the rest goes out as the last block
+        eof_ = true;
+        if (pe_) {                        // cultPEbuf(.., false): both files keep min(#lines) lines -- equal for valid PE
+        }
+        return !t1.empty();
+    }
+    if (!pe_) {                           // cultbuf @0x432530
+        int total = (int)t1.size();
+        t1.push_back(0);
+        int n = get_end_pos(total - (int)first_[0].size(), t1.data(), total, first_[0]);
+        int cut = n + 1;
+        left_[0].assign(t1.data() + cut, total - cut);
+        t1.resize(cut);
+        return true;
+    }
+    // cultPEbuf @0x432180 (cut = true): newline positions of both buffers, back off two lines from the
+    // shorter one, find the record start in file 1, cut file 2 after the same number of lines
+    std::vector<int> nl[2];
+    for (int k = 0; k < 2; k++)
+        for (size_t i = 0; i < t[k]->size(); i++) if ((*t[k])[i] == '\n') nl[k].push_back((int)i);
+    int nmin = (int)std::min(nl[0].size(), nl[1].size());
+    if (nmin < 3) throw std::runtime_error("block too small to cut a paired-end buffer");
+    int e = nmin - 2;
+    int total1 = (int)t1.size();
+    t1.push_back(0);
+    int n = get_end_pos(nl[0][e], t1.data(), total1, first_[0]);
+    t1.pop_back();
+    while (e > 0 && nl[0][e] != n) e--;
+    if (nl[0][e] != n) throw std::runtime_error("paired-end cut failed (no record start found)");
+    int cut1 = n + 1, cut2 = nl[1][e] + 1;
+    left_[0].assign(t1.data() + cut1, t1.size() - cut1);
+    left_[1].assign(t2.data() + cut2, t2.size() - cut2);
+    t1.resize(cut1);
+    t2.resize(cut2);
+    return true;
+}
+
+static void parse_one(const std::vector<char> &t, std::vector<const char *> &line, std::vector<int> &len) {
+    const char *p = t.data(), *end = p + t.size();
+    while (p < end) {
+        const char *q = (const char *)memchr(p, '\n', end - p);
+        if (!q) q = end;
+        line.push_back(p);
+        len.push_back((int)(q - p));
+        p = q + 1;
+    }
+}
+
+void parse_block(const std::vector<char> &t1, const std::vector<char> &t2, bool pe, MemBuf &mb) {
+    mb.ids.clear(); mb.seq.clear(); mb.qual.clear(); mb.idlen.clear(); mb.seqlen.clear();
+    std::vector<const char *> ln[2];
+    std::vector<int> ll[2];
+    parse_one(t1, ln[0], ll[0]);
+    if (pe) parse_one(t2, ln[1], ll[1]);
+    size_t nrec = ln[0].size() / 4;
+    if (ln[0].size() % 4) throw std::runtime_error("FASTQ block is not a multiple of four lines");
+    if (pe && ln[1].size() != ln[0].size()) throw std::runtime_error("paired files disagree in record count");
+    mb.ids.reserve(t1.size() / 4 + t2.size() / 4);
+    mb.seq.reserve((t1.size() + t2.size()) / 2);
+    mb.qual.reserve((t1.size() + t2.size()) / 2);
+    for (size_t r = 0; r < nrec; r++) {
+        for (int k = 0; k < (pe ? 2 : 1); k++) {
+            const char *id = ln[k][4 * r], *sq = ln[k][4 * r + 1], *pl = ln[k][4 * r + 2], *ql = ln[k][4 * r + 3];
+            int il = ll[k][4 * r], sl = ll[k][4 * r + 1], pll = ll[k][4 * r + 2], qll = ll[k][4 * r + 3];
+            if (il < 1 || id[0] != '@' || pll < 1 || pl[0] != '+') throw std::runtime_error("malformed FASTQ record");
+            if (pll != 1) throw std::runtime_error("'+' lines that repeat the ID are not supported");
+            if (sl != qll) throw std::runtime_error("sequence and quality lengths differ");
+            if (il - 1 > 255) throw std::runtime_error("read ID longer than 255 bytes (limit of the reference's name model)");
+            mb.ids.insert(mb.ids.end(), id + 1, id + il);
+            mb.seq.insert(mb.seq.end(), sq, sq + sl);
+            mb.qual.insert(mb.qual.end(), ql, ql + qll);
+            mb.idlen.push_back((uint16_t)(il - 1));
+            mb.seqlen.push_back(sl);
+        }
+    }
+}
+
+bool BlockReader::next(MemBuf &mb) {
+    std::vector<char> t1, t2;
+    if (!next_text(t1, t2)) return false;
+    mb.src_off[0] = off_[0]; mb.src_off[1] = off_[1];
+    mb.src_bytes[0] = t1.size(); mb.src_bytes[1] = t2.size();
+    off_[0] += t1.size(); off_[1] += t2.size();
+    parse_block(t1, t2, pe_, mb);
+    return true;
+}
+
+void render_block(const MemBuf &mb, bool pe, std::string &o1, std::string &o2) {
+    o1.clear(); o2.clear();
+    size_t io = 0, so = 0;
+    for (uint32_t r = 0; r < mb.nreads(); r++) {
+        std::string &o = (pe && (r & 1)) ? o2 : o1;
+        o.push_back('@');
+        o.append((const char *)mb.ids.data() + io, mb.idlen[r]);
+        o.push_back('\n');
+        o.append((const char *)mb.seq.data() + so, mb.seqlen[r]);
+        o.append("\n+\n");
+        o.append((const char *)mb.qual.data() + so, mb.seqlen[r]);
+        o.push_back('\n');
+        io += mb.idlen[r];
+        so += mb.seqlen[r];
+    }
+}
+
+}  // namespace sqhost

@@ -99,6 +99,12 @@ int  sq_load_model(sq_ctx *c, const uint8_t *blob, uint64_t len);
 /* bytes such a snapshot must have for this context's slevel / qlevel / id_rule */
 uint64_t sq_model_size(const sq_ctx *c);
 
+/* SeqArcPreProcess::doPreProcess @0x4153b0 -> encodeForModel @0x4228e0 -> SaveModelToMem @0x420c00:
+ * train the model snapshot on the sample blocks (HOST buffers; models are not reset between them)
+ * and write it to blob[0 .. sq_model_size).  The caller stores it in the .arc trailer and installs it
+ * with sq_load_model. */
+int  sq_train_model(sq_ctx *c, const sq_block_in *blocks, int n, uint8_t *blob, uint64_t cap);
+
 /* doFqzEncode @0x42d2d0 over a batch: HOST buffers in, HOST records out, order preserved.
  * Copies host->device, runs the kernels, copies the records device->host. */
 int  sq_encode_blocks(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out);

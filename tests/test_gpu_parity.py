@@ -125,3 +125,17 @@ def test_md5_mismatch_is_reported(fq):
     d = codec.doDecode([bytes(ref)], raise_on_error=False)[0]
     assert d.status == -10
     codec.close()
+
+
+def test_train_model_matches_reference_snapshot(fq):
+    """encodeForModel on the GPU reproduces the snapshot the reference trained (md5 of its 27 MB blob)."""
+    import hashlib
+    name = "se100_q8_usemodel"
+    m = common.MANIFEST[name]
+    fqtext = common.case_fastq(name)[0]
+    sample = common.preprocess_sample(fqtext, 1 << 20)
+    codec = fq.EncapFqzComp(fq.SeqArcParam(), workspace_bytes=WS)
+    blob = codec.encodeForModel([common.to_membuf(b) for b in sample])
+    assert len(blob) == m["model_bytes"]
+    assert hashlib.md5(blob).hexdigest() == m["model_md5"]
+    codec.close()
