@@ -1,0 +1,253 @@
+// seqarc_b200 -- command-line driver standing where SeqArc's main / SeqArcContext / reader and worker
+// threads stand (main @0x41fd40, doReadAndEncode @0x41a4e0, doTask @0x433dd0), for the no-reference
+// path:  -c -1 a.fq [-2 b.fq] -o out [-l r] [-n] [-f]      ->  out.arc
+//        -d in.arc -o out [-f]                                ->  out.fastq | out_1.fastq + out_2.fastq
+// FASTQ parsing, block cutting and .arc packing run here on the host; every coder runs on the GPU
+// behind the C ABI of include/seqarc_b200.h.  ./seqarc.config (BlockSize(M), Slevel, Qlevel) is read
+// like the reference does (parseOptFromFile @0x4062e0) because none of the three is stored in the .arc.
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/seqarc_b200.h"
+#include "arc_file.h"
+#include "fastq_block.h"
+
+using namespace sqhost;
+
+struct Opt {
+    bool compress = false, decompress = false, force = false, md5 = true, lossy = false;
+    double lossy_r = 0;
+    std::string in1, in2, out, arc;
+    int block_mb = 50, slevel = 3, qlevel = 2, device = 0, batch = 0;
+    bool verbose = false;
+};
+
+static void read_config(Opt &o) {
+    FILE *f = fopen("./seqarc.config", "r");
+    if (!f) return;
+    char line[256];
+    while (fgets(line, sizeof line, f)) {
+        char *c = strchr(line, ':');
+        if (!c) continue;
+        *c = 0;
+        int v = atoi(c + 1);
+        if (!strcmp(line, "BlockSize(M)")) o.block_mb = v;
+        else if (!strcmp(line, "Slevel")) o.slevel = v;
+        else if (!strcmp(line, "Qlevel")) o.qlevel = v;
+    }
+    fclose(f);
+}
+
+static std::string base_name(const std::string &p) {
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? p : p.substr(k + 1);
+}
+static uint64_t file_size(const std::string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 ? (uint64_t)st.st_size : 0;
+}
+static bool exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+
+static void die(const std::string &m) { fprintf(stderr, "seqarc_b200: %s\n", m.c_str()); exit(1); }
+
+static sq_ctx *make_ctx(const Opt &o, bool usemodel, bool lossy, double r, bool md5, int id_rule) {
+    sq_params p{};
+    p.device = o.device; p.usemodel = usemodel; p.lossy = lossy; p.lossy_r = r; p.md5 = md5;
+    p.slevel = o.slevel; p.qlevel = o.qlevel; p.id_rule = id_rule;
+    sq_ctx *c = nullptr;
+    if (sq_create(&p, &c) != SQ_OK) die(std::string("sq_create: ") + sq_last_error(nullptr));
+    return c;
+}
+
+static sq_block_in as_in(const MemBuf &m) {
+    sq_block_in b{};
+    b.nreads = m.nreads();
+    b.ids = m.ids.data(); b.seq = m.seq.data(); b.qual = m.qual.data();
+    b.idlen = m.idlen.data(); b.seqlen = m.seqlen.data();
+    b.idbytes = m.ids.size(); b.seqbytes = m.seq.size();
+    return b;
+}
+
+// SeqArcPreProcess::doPreProcess @0x4153b0: the (up to five) head blocks the snapshot is trained on.
+// Each sample block takes whole records until it holds at least BlockSize bytes (single-end; measured
+// against the reference: 5 x 4298 reads of 244 B at BlockSize 1 MiB).
+static void sample_blocks(const Opt &o, std::vector<MemBuf> &out) {
+    if (!o.in2.empty()) die("usemodel training for paired-end input is not implemented yet");
+    FILE *f = fopen(o.in1.c_str(), "rb");
+    if (!f) die("cannot open " + o.in1);
+    uint64_t bs = (uint64_t)o.block_mb << 20;
+    std::vector<char> text;
+    char *line = nullptr;
+    size_t cap = 0;
+    for (int b = 0; b < 5; b++) {
+        text.clear();
+        while (text.size() < bs) {
+            bool okrec = true;
+            for (int k = 0; k < 4; k++) {
+                ssize_t n = getline(&line, &cap, f);
+                if (n <= 0) { okrec = false; break; }
+                text.insert(text.end(), line, line + n);
+            }
+            if (!okrec) break;
+        }
+        if (text.empty()) break;
+        out.emplace_back();
+        std::vector<char> none;
+        parse_block(text, none, false, out.back());
+    }
+    free(line);
+    fclose(f);
+}
+
+static int do_compress(const Opt &o) {
+    std::string arcname = o.out + ".arc";
+    if (exists(arcname) && !o.force) die(arcname + " exists (use -f)");
+    bool pe = !o.in2.empty();
+    uint64_t total = file_size(o.in1) + (pe ? file_size(o.in2) : 0);
+    // doCheckSetEncodeOpt @0x408104-0x40831f: usemodel when total * 0.0023947358 > 33,693,269; off for Qlevel > 2
+    bool usemodel = (double)total * 0.0023947358 > 33693269.0 && o.qlevel <= 2;
+    if (getenv("SQ_FORCE_USEMODEL")) usemodel = atoi(getenv("SQ_FORCE_USEMODEL")) != 0;
+    ArcParams ap;
+    ap.pe = pe; ap.usemodel = usemodel; ap.lossy = o.lossy; ap.md5 = o.md5;
+    ap.name1 = base_name(o.in1); ap.name2 = base_name(o.in2);
+    // ID-bin analysis (IDProcess::analysisIDBinType @0x4310a0) is not restated: IDs always take the
+    // name-model path (idbin all zero), which every SeqArc decoder reads.
+    sq_ctx *c = make_ctx(o, usemodel, o.lossy, o.lossy_r, o.md5, 0);
+    if (usemodel) {
+        std::vector<MemBuf> sample;
+        sample_blocks(o, sample);
+        std::vector<sq_block_in> in;
+        for (auto &m : sample) in.push_back(as_in(m));
+        ap.model.resize(sq_model_size(c));
+        if (sq_train_model(c, in.data(), (int)in.size(), ap.model.data(), ap.model.size()) != SQ_OK)
+            die(std::string("training: ") + sq_last_error(c));
+        if (sq_load_model(c, ap.model.data(), ap.model.size()) != SQ_OK) die(sq_last_error(c));
+    }
+    BlockReader rd(o.in1, o.in2, (uint64_t)o.block_mb << 20);
+    if (!rd.ok()) die("cannot open input");
+    ArcWriter wr;
+    if (!wr.open(arcname)) die("cannot create " + arcname);
+    int batch = o.batch > 0 ? o.batch : 64;
+    std::vector<MemBuf> mbs;
+    std::vector<std::vector<uint8_t>> recs;
+    uint64_t nblocks = 0, in_bytes = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (bool more = true; more;) {
+        mbs.clear();
+        while ((int)mbs.size() < batch) {
+            mbs.emplace_back();
+            if (!rd.next(mbs.back())) { mbs.pop_back(); more = false; break; }
+        }
+        if (mbs.empty()) break;
+        int n = (int)mbs.size();
+        std::vector<sq_block_in> in(n);
+        std::vector<sq_block_out> out(n);
+        recs.resize(n);
+        for (int i = 0; i < n; i++) {
+            in[i] = as_in(mbs[i]);
+            recs[i].resize(mbs[i].ids.size() + 2 * mbs[i].seq.size() + 8 * (size_t)mbs[i].nreads() + 4096);
+            out[i] = {recs[i].data(), recs[i].size(), 0, 0};
+        }
+        int rc = sq_encode_blocks(c, in.data(), n, out.data());
+        if (rc != SQ_OK) die(std::string("encode: ") + sq_last_error(c) + " (status " + std::to_string(rc) + ")");
+        for (int i = 0; i < n; i++) {
+            wr.add_block(recs[i].data(), out[i].len, mbs[i].src_bytes, mbs[i].src_off);
+            in_bytes += mbs[i].src_bytes[0] + mbs[i].src_bytes[1];
+        }
+        nblocks += n;
+    }
+    if (!wr.finish(ap)) die("write failed");
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (o.verbose)
+        fprintf(stderr, "blocks %llu  in %llu B  out %llu B  ratio %.3f  usemodel %d  %.2f s\n", (unsigned long long)nblocks,
+                (unsigned long long)in_bytes, (unsigned long long)wr.bytes(), wr.bytes() ? (double)in_bytes / wr.bytes() : 0.0, (int)usemodel, s);
+    sq_destroy(c);
+    return 0;
+}
+
+static int do_decompress(const Opt &o) {
+    ArcReader ar;
+    if (!ar.load(o.arc)) die(ar.err);
+    if (ar.p.idbin[0]) die("archive uses the rule-based ID path (IDProcess::decodeIDS), which is not implemented yet");
+    bool pe = ar.p.pe;
+    std::string n1 = pe ? o.out + "_1.fastq" : o.out + ".fastq", n2 = o.out + "_2.fastq";
+    if (!o.force && (exists(n1) || (pe && exists(n2)))) die("output exists (use -f)");
+    sq_ctx *c = make_ctx(o, ar.p.usemodel, ar.p.lossy, 1.5, ar.p.md5, 0);
+    if (ar.p.usemodel && sq_load_model(c, ar.p.model.data(), ar.p.model.size()) != SQ_OK) die(sq_last_error(c));
+    FILE *f1 = fopen(n1.c_str(), "wb"), *f2 = pe ? fopen(n2.c_str(), "wb") : nullptr;
+    if (!f1 || (pe && !f2)) die("cannot create output");
+    int batch = o.batch > 0 ? o.batch : 64;
+    std::string o1, o2;
+    for (size_t b0 = 0; b0 < ar.idx.size(); b0 += batch) {
+        int n = (int)std::min<size_t>(batch, ar.idx.size() - b0);
+        std::vector<const uint8_t *> recs(n);
+        std::vector<uint64_t> lens(n);
+        std::vector<sq_block_dec> dec(n);
+        std::vector<MemBuf> mbs(n);
+        for (int i = 0; i < n; i++) {
+            const BlockIndex &bi = ar.idx[b0 + i];
+            recs[i] = ar.data.data() + bi.arc_off;
+            lens[i] = bi.len;
+            uint64_t src = (uint64_t)bi.src_bytes[0] + bi.src_bytes[1];
+            MemBuf &m = mbs[i];
+            m.ids.resize(src + 64); m.seq.resize(src / 2 + 64); m.qual.resize(src / 2 + 64);
+            uint32_t rcap = (uint32_t)(src / 6 + 16);
+            m.idlen.resize(rcap); m.seqlen.resize(rcap);
+            dec[i] = {m.ids.data(), m.ids.size(), m.seq.data(), m.qual.data(), m.seq.size(), m.idlen.data(), m.seqlen.data(), rcap, 0, 0, 0, 0};
+        }
+        int rc = sq_decode_blocks(c, recs.data(), lens.data(), n, dec.data());
+        if (rc != SQ_OK) {
+            const char *w = rc == SQ_ERR_MD5_NAME ? "Name md5 unequal" : rc == SQ_ERR_MD5_SEQ ? "Seq md5 unequal" : rc == SQ_ERR_MD5_QUAL ? "Qual md5 unequal" : sq_last_error(c);
+            die(std::string("decode: ") + w);
+        }
+        for (int i = 0; i < n; i++) {
+            MemBuf &m = mbs[i];
+            m.idlen.resize(dec[i].nreads); m.seqlen.resize(dec[i].nreads);
+            render_block(m, pe, o1, o2);
+            fwrite(o1.data(), 1, o1.size(), f1);
+            if (pe) fwrite(o2.data(), 1, o2.size(), f2);
+        }
+    }
+    fclose(f1);
+    if (f2) fclose(f2);
+    sq_destroy(c);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    Opt o;
+    read_config(o);
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value after " + a); return argv[++i]; };
+        if (a == "-c") o.compress = true;
+        else if (a == "-d") o.decompress = true;
+        else if (a == "-f") o.force = true;
+        else if (a == "-n") o.md5 = false;
+        else if (a == "-v") o.verbose = true;
+        else if (a == "-t") val();                      // worker threads: the GPU takes whole batches instead
+        else if (a == "-1") o.in1 = val();
+        else if (a == "-2") o.in2 = val();
+        else if (a == "-o") o.out = val();
+        else if (a == "-l") { o.lossy = true; o.lossy_r = atof(val().c_str()); }
+        else if (a == "-g") o.device = atoi(val().c_str());
+        else if (a == "-b") o.batch = atoi(val().c_str());
+        else if (a == "-h") { printf("usage: seqarc_b200 -c -1 a.fq [-2 b.fq] -o out [-l r] [-n] [-f] | -d in.arc -o out [-f]\n"); return 0; }
+        else if (a[0] != '-') o.arc = a;
+        else die("unknown option " + a);
+    }
+    try {
+        if (o.compress && !o.in1.empty() && !o.out.empty()) return do_compress(o);
+        if (o.decompress && !o.arc.empty() && !o.out.empty()) return do_decompress(o);
+    } catch (const std::exception &e) {
+        die(e.what());
+    }
+    die("nothing to do (see -h)");
+}

@@ -1,0 +1,85 @@
+"""GPU: the host driver (fastqueeze_b200/seqarc_b200: C++ block cutter + .arc packer over the C ABI).
+
+Whole-file contract of BASELINE.json: a GPU-written .arc is byte-identical to what the reference writes
+at -t 1, decodes with the reference decompressor, and reference-written archives decode here."""
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from tests import common
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
+
+# archives whose IDs the reference codes with the name model (idbin all zero): byte identity expected
+IDENTICAL = ["illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
+             "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel"]
+
+
+def _setup(name, d):
+    m = common.MANIFEST[name]
+    fq = common.case_fastq(name)
+    paths = []
+    for k, t in enumerate(fq):
+        # same base names as when the golden was made (they are stored in the trailer)
+        p = os.path.join(d, "in_%d.fq" % (k + 1))
+        open(p, "wb").write(t)
+        paths.append(p)
+    cfg = m["config"] or {}
+    if cfg:
+        with open(os.path.join(d, "seqarc.config"), "w") as f:
+            for k, v in cfg.items():
+                f.write("%s:%s\n" % (k, v))
+    return m, fq, paths
+
+
+def _compress(m, paths, d, out="out"):
+    args = [CLI, "-c", "-f", "-1", paths[0]] + (["-2", paths[1]] if m["pe"] else []) + ["-o", out] + m["opts"]
+    env = dict(os.environ)
+    if m.get("usemodel"):
+        env["SQ_FORCE_USEMODEL"] = "1"       # the golden was made with the size-faking shim
+    r = subprocess.run(args, cwd=d, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    return open(os.path.join(d, out + ".arc"), "rb").read()
+
+
+@pytest.mark.parametrize("name", IDENTICAL)
+def test_cli_archive_is_byte_identical_to_reference(name):
+    with tempfile.TemporaryDirectory() as d:
+        m, fq, paths = _setup(name, d)
+        arc = _compress(m, paths, d)
+    assert len(arc) == m["arc_bytes"]
+    assert hashlib.md5(arc).hexdigest() == m["arc_md5"]
+
+
+@pytest.mark.parametrize("name", [c for c in common.CASES if "lossy" not in c])
+def test_cli_decodes_reference_archive(name):
+    kw, _ = common.case_params(name)
+    if kw["id_rule"]:
+        pytest.skip("rule-based ID regeneration (IDProcess::decodeIDS) is a 'next' row")
+    with tempfile.TemporaryDirectory() as d:
+        m, fq, paths = _setup(name, d)
+        open(os.path.join(d, "ref.arc"), "wb").write(common.case_archive(name))
+        r = subprocess.run([CLI, "-d", "-f", "ref.arc", "-o", "back"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs = ["back_1.fastq", "back_2.fastq"] if m["pe"] else ["back.fastq"]
+        for o, t in zip(outs, fq):
+            assert open(os.path.join(d, o), "rb").read() == t
+
+
+@pytest.mark.parametrize("name", ["err_pe1000", "srr_pe100", "illumina_pe150_n", "se100_q8_3blocks"])
+def test_reference_decodes_cli_archive(name):
+    if not po.have_ref():
+        pytest.skip("reference binary not staged")
+    with tempfile.TemporaryDirectory() as d:
+        m, fq, paths = _setup(name, d)
+        _compress(m, paths, d, out="mine")
+        rc, log = po.run_ref(["-d", "-f", "mine.arc", "-o", "back"], d, config=m["config"])
+        assert rc == 0, log[-1500:]
+        outs = ["back_1.fastq", "back_2.fastq"] if m["pe"] else ["back.fastq"]
+        for o, t in zip(outs, fq):
+            assert open(os.path.join(d, o), "rb").read() == t

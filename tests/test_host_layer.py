@@ -1,0 +1,89 @@
+"""CPU: the host C++ layer (host/: block cutter, .arc container) against archives the reference wrote."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import common
+from oracle import arcwalk
+
+HOSTLIB = os.path.join(common.ROOT, "fastqueeze_b200", "libseqarc_host.so")
+
+
+@pytest.fixture(scope="module")
+def hl():
+    import __graft_entry__
+    if not os.path.exists(HOSTLIB):
+        __graft_entry__.build()
+    L = C.CDLL(HOSTLIB)
+    L.sqh_cut_blocks.restype = C.c_int
+    L.sqh_cut_blocks.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.sqh_write_arc.restype = C.c_int
+    L.sqh_write_arc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p,
+                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    return L
+
+
+def _write_inputs(name, d):
+    fq = common.case_fastq(name)
+    paths = []
+    for k, t in enumerate(fq):
+        p = os.path.join(d, "in_%d.fq" % (k + 1))
+        open(p, "wb").write(t)
+        paths.append(p)
+    return paths
+
+
+@pytest.mark.parametrize("name", ["se100_q8_3blocks", "illumina_pe150_3blocks", "se100_q8_usemodel", "illumina_pe150", "err_pe1000"])
+def test_block_cutter_matches_reference_index(hl, name):
+    """Same reads per block and same source byte ranges as the reference's reader (getEndPos / cultbuf / cultPEbuf)."""
+    m = common.MANIFEST[name]
+    arc = arcwalk.parse_arc(common.case_archive(name))
+    idx = arcwalk.block_index(arc, m["pe"])
+    bs = int((m["config"] or {}).get("BlockSize(M)", 50)) << 20
+    with tempfile.TemporaryDirectory() as d:
+        paths = _write_inputs(name, d)
+        cap = 64
+        nr, s1, s2 = np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        n = hl.sqh_cut_blocks(paths[0].encode(), paths[1].encode() if m["pe"] else None, bs,
+                              nr.ctypes.data, s1.ctypes.data, s2.ctypes.data, cap)
+    assert n == len(arc["blocks"])
+    want_reads = [int.from_bytes(b["streams"][1], "little") for b in arc["blocks"]]
+    assert list(nr[:n]) == want_reads
+    if m["pe"]:
+        assert [(int(a), int(b)) for a, b in zip(s1[:n], s2[:n])] == [(r["src1"], r["src2"]) for r in idx]
+    else:
+        assert [int(a) for a in s1[:n]] == [r["src2"] for r in idx]      # SE record: (len*2, 1, src bytes, 0)
+
+
+@pytest.mark.parametrize("name", common.CASES)
+def test_arc_writer_reproduces_reference_file(hl, name):
+    """Re-packing the reference's own block records with ArcWriter gives the reference's file byte for byte."""
+    m = common.MANIFEST[name]
+    data = common.case_archive(name)
+    arc = arcwalk.parse_arc(data)
+    idx = arcwalk.block_index(arc, m["pe"])
+    recs = b"".join(b["raw"] for b in arc["blocks"])
+    lens = np.array([len(b["raw"]) for b in arc["blocks"]], np.uint64)
+    if m["pe"]:
+        s1 = np.array([r["src1"] for r in idx], np.uint64)
+        s2 = np.array([r["src2"] for r in idx], np.uint64)
+    else:
+        s1 = np.array([r["src2"] for r in idx], np.uint64)
+        s2 = None
+    params = arc["trailer"]["params"]
+    idbin = np.frombuffer(params[15], np.uint8).copy()
+    model = arc["trailer"].get("model")
+    mb = np.frombuffer(model[4:], np.uint8).copy() if model else None
+    ra = np.frombuffer(recs, np.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.arc")
+        r = hl.sqh_write_arc(out.encode(), int(m["pe"]), int(params[6][0]), int(params[16][0]), int(params[17][0]),
+                             params[13], params.get(14, b""), idbin.ctypes.data, mb.ctypes.data if mb is not None else None,
+                             0 if mb is None else mb.shape[0], ra.ctypes.data, lens.ctypes.data, s1.ctypes.data,
+                             s2.ctypes.data if s2 is not None else None, len(lens))
+        assert r == 0
+        got = open(out, "rb").read()
+    assert got == data

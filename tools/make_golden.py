@@ -34,6 +34,8 @@ CASES = [
     dict(name="se100_q8", src=dict(kind="se100_q8", n_templates=4000, seed=12345), pe=False, opts=[], config=None),
     dict(name="se100_q8_3blocks", src=dict(kind="se100_q8", n_templates=12000, seed=5), pe=False, opts=[],
          config={"BlockSize(M)": 1}),
+    dict(name="illumina_pe150_3blocks", src=dict(kind="illumina_pe150", n_templates=3200, seed=31), pe=True, opts=[],
+         config={"BlockSize(M)": 1}),
     dict(name="srr_pe100", src=dict(kind="srr_pe100", n_templates=1200, seed=3), pe=True, opts=[], config=None),
     dict(name="illumina_pe150_q1", src=dict(kind="illumina_pe150", n_templates=800, seed=21, hash_tail=0.1), pe=True, opts=[],
          config={"Qlevel": 1}),
