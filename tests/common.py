@@ -26,20 +26,29 @@ def case_fastq(name):
     return t if m["pe"] else (t,)
 
 
-def preprocess_sample(fastq: bytes, blocksize: int, max_blocks: int = 5):
-    """The reads SeqArcPreProcess::doPreProcess @0x4153b0 trains the model snapshot on (SE): up to five head
-    blocks, each taking whole records until it holds at least `blocksize` bytes (measured against the
-    reference: 5 x 4298 reads of 244 B at BlockSize 1 MiB, one more read per block than the encoder's blocks)."""
+def preprocess_sample(fastq, blocksize: int, max_blocks: int = 5, fastq2=None):
+    """The reads SeqArcPreProcess::doPreProcess @0x4153b0 trains the model snapshot on: up to five head
+    blocks, each taking whole records until it holds at least `blocksize` bytes (BlockSize / 2 of mate 1
+    for paired-end, the same number of records from mate 2).  Measured against the reference with the
+    size-faking shim: 5 x 4298 reads of 244 B (SE) / 5 x 1461 pairs of 359 B per mate (PE) at BlockSize 1 MiB,
+    i.e. one more record per block than the encoder's blocks hold."""
     recs = po.parse_fastq(fastq)
+    recs2 = po.parse_fastq(fastq2) if fastq2 is not None else None
+    quota = blocksize // 2 if recs2 is not None else blocksize
     out, i = [], 0
     for _ in range(max_blocks):
         if i >= len(recs):
             break
         size, j = 0, i
-        while j < len(recs) and size < blocksize:
+        while j < len(recs) and size < quota:
             size += len(recs[j][0]) + len(recs[j][1]) + len(recs[j][2]) + 6
             j += 1
-        out.append(po.block_from_records(recs[i:j]))
+        if recs2 is None:
+            out.append(po.block_from_records(recs[i:j]))
+        else:
+            inter = [None] * (2 * (j - i))
+            inter[0::2], inter[1::2] = recs[i:j], recs2[i:j]
+            out.append(po.block_from_records(inter))
         i = j
     return out
 
@@ -55,9 +64,8 @@ def case_model(name):
         m = MANIFEST[name]
         bs = int((m["config"] or {}).get("BlockSize(M)", 50)) << 20
         fq = case_fastq(name)
-        assert not m["pe"]
         o = po.Oracle(usemodel=0, id_rule=0)
-        blob = o.train(preprocess_sample(fq[0], bs))
+        blob = o.train(preprocess_sample(fq[0], bs, fastq2=fq[1] if m["pe"] else None))
         assert hashlib.md5(blob).hexdigest() == m["model_md5"], "oracle-trained snapshot differs from the reference's"
         _MODEL_CACHE[name] = blob
     return _MODEL_CACHE[name]
@@ -104,8 +112,10 @@ def case_blocks(name):
     for i, b in enumerate(arc["blocks"]):
         if nb == 1:
             parts = fq
-        else:   # cut the source text at the offsets the reference recorded in its block index
-            assert not m["pe"]
+        elif m["pe"]:   # cut both source texts at the offsets the reference recorded in its block index
+            s1, s2 = idx[i]["offs"][1], idx[i]["offs"][2]
+            parts = (fq[0][s1:s1 + idx[i]["src1"]], fq[1][s2:s2 + idx[i]["src2"]])
+        else:
             s = idx[i]["offs"][1]
             e = idx[i + 1]["offs"][1] if i + 1 < nb else len(fq[0])
             parts = (fq[0][s:e],)

@@ -17,7 +17,7 @@ CLI = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
 
 # archives whose IDs the reference codes with the name model (idbin all zero): byte identity expected
 IDENTICAL = ["illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
-             "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel"]
+             "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel", "illumina_pe150_usemodel"]
 
 
 def _setup(name, d):

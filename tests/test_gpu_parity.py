@@ -130,10 +130,15 @@ def test_md5_mismatch_is_reported(fq):
 def test_train_model_matches_reference_snapshot(fq):
     """encodeForModel on the GPU reproduces the snapshot the reference trained (md5 of its 27 MB blob)."""
     import hashlib
-    name = "se100_q8_usemodel"
+    for name in ("se100_q8_usemodel", "illumina_pe150_usemodel"):
+        _train_case(fq, name)
+
+
+def _train_case(fq, name):
+    import hashlib
     m = common.MANIFEST[name]
-    fqtext = common.case_fastq(name)[0]
-    sample = common.preprocess_sample(fqtext, 1 << 20)
+    t = common.case_fastq(name)
+    sample = common.preprocess_sample(t[0], 1 << 20, fastq2=t[1] if m["pe"] else None)
     codec = fq.EncapFqzComp(fq.SeqArcParam(), workspace_bytes=WS)
     blob = codec.encodeForModel([common.to_membuf(b) for b in sample])
     assert len(blob) == m["model_bytes"]

@@ -43,6 +43,8 @@ CASES = [
     # (27 MB model blob) -> only the block records, the block index and the md5 of the model blob are kept
     dict(name="se100_q8_usemodel", src=dict(kind="se100_q8", n_templates=14000, seed=77), pe=False, opts=[],
          config={"BlockSize(M)": 1}, fake_size=15000000000),
+    dict(name="illumina_pe150_usemodel", src=dict(kind="illumina_pe150", n_templates=3200, seed=41), pe=True, opts=[],
+         config={"BlockSize(M)": 1}, fake_size=8000000000),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
