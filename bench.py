@@ -270,12 +270,41 @@ def main():
                 idlen=torch.empty_like(b["idlen"]), seqlen=torch.empty_like(b["seqlen"])) for b in blocks]
 
     stream = torch.cuda.current_stream()
+    # the reference turns usemodel on above 14,069,722,771 input bytes (doCheckSetEncodeOpt @0x408104): the full
+    # configs[1] job is above that, so it runs from a snapshot trained on the five head sample blocks
+    usemodel = int(fastq_bytes * 0.0023947358 > 33693269.0)
     p = _lib.SqParams()
     p.device, p.md5, p.slevel, p.qlevel, p.id_rule, p.stream = local, 1, 3, 2, 0, stream.cuda_stream
+    p.usemodel = usemodel
     h = C.c_void_p()
     r = L_.sq_create(C.byref(p), C.byref(h))
     if r:
         raise SystemExit("sq_create failed: %d %s" % (r, L_.sq_last_error(None)))
+
+    if usemodel:
+        # SeqArcPreProcess sample: 5 blocks of ceil(BlockSize/2 / record) pairs = the first 5 * (PAIRS_PER_BLOCK + 1) pairs
+        t0 = time.perf_counter()
+        npairs = 5 * (PAIRS_PER_BLOCK + 1)
+        cat = {k: torch.cat([blocks[i][k] for i in range(6)]) for k in ("ids", "seq", "qual", "idlen", "seqlen")}
+        samp = {"ids": cat["ids"][:2 * npairs * ID_W], "seq": cat["seq"][:2 * npairs * L], "qual": cat["qual"][:2 * npairs * L],
+                "idlen": cat["idlen"][:2 * npairs], "seqlen": cat["seqlen"][:2 * npairs], "nreads": 2 * npairs}
+        hs = to_host(torch, samp)
+        del cat, samp
+        sin = (_lib.SqBlockIn * 1)()
+        sin[0].nreads = hs["nreads"]
+        sin[0].ids, sin[0].seq, sin[0].qual = hs["ids"].ctypes.data, hs["seq"].ctypes.data, hs["qual"].ctypes.data
+        sin[0].idlen, sin[0].seqlen = hs["idlen"].ctypes.data, hs["seqlen"].ctypes.data
+        sin[0].idbytes, sin[0].seqbytes = hs["ids"].shape[0], hs["seq"].shape[0]
+        blob = np.empty(int(L_.sq_model_size(h)), np.uint8)
+        r = L_.sq_train_model(h, sin, 1, blob.ctypes.data, blob.shape[0])
+        if r:
+            raise SystemExit("train failed: %d %s" % (r, L_.sq_last_error(h)))
+        r = L_.sq_load_model(h, blob.ctypes.data, blob.shape[0])
+        if r:
+            raise SystemExit("load model failed: %d %s" % (r, L_.sq_last_error(h)))
+        log("rank %d: trained the %d-byte model snapshot on %d pairs in %.1fs (pre-process, untimed)"
+            % (rank, blob.shape[0], npairs, time.perf_counter() - t0))
+        del hs
 
     ins = (_lib.SqBlockIn * nblocks)()
     outs = (_lib.SqBlockOut * nblocks)()
@@ -433,6 +462,8 @@ def main():
         # algorithmic HBM bytes of the whole path per input FASTQ byte (DESIGN.md / SURVEY 8d):
         #   compress 1.9 B/B (read id+seq+qual once, write the record, per-block model reset), decompress the same
         alg_bytes = ALG_BYTES.get(top, ALG_BYTES_DEFAULT)(fastq_bytes, in_bytes, arc_bytes, nblocks)
+        if top == "dec.decode" and usemodel:
+            alg_bytes += nblocks * 27_203_584          # the snapshot is read once per block to restore the models
         achieved = alg_bytes / 1e9 / (mean_ms[top] / 1e3)
         out = {
             "metric": "FASTQ MB/s compress+decompress (entropy stage)", "value": round(value, 2), "unit": "MB/s",
@@ -440,7 +471,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16/u32 integer",
             "data": "synthetic",
             "config": {"workload": workload, "fastq_MB_per_gpu": round(fastq_bytes / 1e6, 1), "blocks_per_gpu": nblocks,
-                       "ratio": round(fastq_bytes / arc_bytes, 3), "l2": "inputs larger than L2 (>= 52 MB per block stream set; no flush)",
+                       "ratio": round(fastq_bytes / arc_bytes, 3), "usemodel": usemodel, "l2": "inputs larger than L2 (>= 52 MB per block stream set; no flush)",
                        "wave_blocks": int(L_.sq_last_wave_blocks(h))},
             "compress_MBps": round(world * fastq_bytes / 1e6 / (enc_ms / 1e3), 2) if enc_ms else None,
             "decompress_MBps": round(world * fastq_bytes / 1e6 / (dec_ms / 1e3), 2) if dec_ms else None,
