@@ -346,12 +346,16 @@ SQ_D int decode_name(u32 *nametab, RcDecW &rc, u8 *name_out, u64 room, NameSmem 
 }
 
 // one base (inlined four times in decode_seq @0x4296b0); whole warp, uniform.
-// The 256 contexts reachable in four more bases are one contiguous KiB of the table: every step
-// the warp copies that KiB asynchronously (cp.async, L2 -> shared) into an 8-slot ring and reads
-// the counters it needs NOW from the slot filled four steps ago, so the table's L2 / HBM latency is
-// off the symbol chain.  Counters updated during those four steps are forwarded from a 4-entry log.
-// Every lane stores the updated counters (same value, same address): each lane later reads its own
-// store, and __syncwarp orders it before the other lanes' later copies.
+// The 4^SQ_LOOK contexts reachable SQ_LOOK bases ahead are contiguous in the table: every step the
+// warp copies them asynchronously (cp.async, L2 -> shared) into an 8-slot ring and reads the counters
+// it needs NOW from the slot filled SQ_LOOK steps ago, so the table's L2 / HBM latency is off the
+// symbol chain.  SQ_LOOK = 2 (64 B per base): at ~600 cycles per base two steps cover an HBM round
+// trip; four steps (1 KiB per base) measured 6.9 TB of DRAM reads per 14 GB job for no gain.
+// Counters updated during the look-ahead window are forwarded from a 4-entry log.  Every lane stores
+// the updated counters (same value, same address): each lane later reads its own store, and
+// __syncwarp orders it before the other lanes' later copies.
+#define SQ_LOOK 2
+#define SQ_LOOK_N (1 << (2 * SQ_LOOK))          // contexts per ring slot
 struct SeqPipe {
     u32 step;
     u32 lc0, lc1, lc2, lc3, lv0, lv1, lv2, lv3;      // last four updated (context, counters), 0 = newest
@@ -359,20 +363,19 @@ struct SeqPipe {
 };
 
 SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane) {
-    {
-        u32 base4 = (last << 8) & mask;
-        const u8 *src = seqtab + ((u64)base4 << 2) + lane * 32;
-        u32 dst = (u32)__cvta_generic_to_shared(ring + ((P.step + 4) & 7) * 256 + lane * 8);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                     "cp.async.cg.shared.global [%2], [%3], 16;\n"
-                     "cp.async.commit_group;\n" ::"r"(dst), "l"(src), "r"(dst + 16), "l"(src + 16) : "memory");
+    if (lane < SQ_LOOK_N / 4) {
+        u32 basec = (last << (2 * SQ_LOOK)) & mask;
+        const u8 *src = seqtab + ((u64)basec << 2) + lane * 16;
+        u32 dst = (u32)__cvta_generic_to_shared(ring + ((P.step + SQ_LOOK) & 7) * SQ_LOOK_N + lane * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
     u32 *S4 = (u32 *)(seqtab + (u64)last * 4);
     u32 x;
-    if (nb >= 4) {
-        asm volatile("cp.async.wait_group 4;\n" ::: "memory");
+    if (nb >= SQ_LOOK) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(SQ_LOOK) : "memory");
         __syncwarp();
-        x = ring[(P.step & 7) * 256 + (last & 255)];
+        x = ring[(P.step & 7) * SQ_LOOK_N + (last & (SQ_LOOK_N - 1))];
     } else {
         x = *S4;
     }
@@ -433,7 +436,7 @@ struct KModelD {
     }
 };
 struct MainSmem {
-    u32 ring[8 * 256];         // base-model candidate ring of the seq warp
+    u32 ring[8 * 256];         // base-model candidate ring of the seq warp (8 slots x up to 256 contexts)
     u32 rlut[1024];            // reciprocal estimates of every possible base-model total (<= 1020)
     NameSmem ns;
     SmModel<2> tip;
