@@ -205,7 +205,7 @@ BlkCost block_cost(const sq_ctx *c, const sq_block_in &b, bool host) {
     k.eb[ST_QUAL] = b.seqbytes + n;
     k.eb[ST_NAME] = c->p.id_rule ? 0 : b.idbytes + 3 * n;
     k.obuf = 0;
-    for (int s = 0; s < ST_COUNT; s++) k.obuf += al16(2 * k.eb[s] + 16);
+    for (int s = 0; s < ST_COUNT; s++) k.obuf += al16(k.eb[s] + k.eb[s] / 2 + 256);
     k.side = al16(16 * n + b.seqbytes / 2 + 4096);
     k.rec = al16(256 + b.idbytes + 2 * b.seqbytes + 8 * n);
     return k;
@@ -221,7 +221,7 @@ struct WaveAcc {
         u64 t = lin + 64 * 1024;
         u64 me = 0, ms = 0, mt = 0;
         for (int s = 0; s < ST_COUNT; s++) {
-            t += 8 * sumeb[s] + 256;
+            t += (s == ST_SEQ ? 4 : 8) * sumeb[s] + 256;
             me = std::max(me, sumeb[s]);
             ms = std::max(ms, segsum[s]);
             mt = std::max(mt, (maxeb[s] + SQ_TILE - 1) / SQ_TILE);
@@ -284,7 +284,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
             sum[s] += k.eb[s];
             w.maxbound[s] = std::max(w.maxbound[s], k.eb[s]);
             segsum[s] += std::min<u64>(k.eb[s], nctx[s]);
-            d.obase[s] = osum; osum += al16(2 * k.eb[s] + 16);
+            d.obase[s] = osum; d.ocap[s] = al16(k.eb[s] + k.eb[s] / 2 + 256); osum += d.ocap[s];
         }
         d.sidebase = sidesum; d.sidecap = k.side; sidesum += k.side;
         d.reccap = k.rec; recsum += k.rec;
@@ -310,7 +310,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     u64 maxsum = std::max(sum[0], std::max(sum[1], sum[2]));
     w.elemA = (u64 *)need(take<u64>(A, maxsum + 1));
     w.elemB = (u64 *)need(take<u64>(A, maxsum + 1));
-    for (int s = 0; s < ST_COUNT; s++) w.triples[s] = (u64 *)need(take<u64>(A, sum[s] + 1));
+    for (int s = 0; s < ST_COUNT; s++) w.triples[s] = (u64 *)need(A.take((s == ST_SEQ ? 4 : 8) * (sum[s] + 2)));
     u64 maxtiles = 0;
     for (int s = 0; s < ST_COUNT; s++) maxtiles = std::max(maxtiles, (w.maxbound[s] + SQ_TILE - 1) / SQ_TILE);
     w.hist = (u32 *)need(take<u32>(A, (u64)n * (1u << SQ_SORT_BITS) * maxtiles + 1));
@@ -591,7 +591,14 @@ extern "C" int sq_debug_fetch(sq_ctx *c, int what, int block, void *dst, uint64_
     if (what < 0 || what > 2) return SQ_ERR_ARG;
     u64 bytes = 8ull * bs.nsym[what];
     if (bytes > cap) return SQ_ERR_CAPACITY;
-    CUDA_OK(c, cudaMemcpy(dst, c->last.triples[what] + c->last_bd[block].ebase[what], bytes, cudaMemcpyDeviceToHost));
+    if (what == ST_SEQ) {                 // packed 32-bit triples: expand to the common 64-bit form
+        std::vector<u32> tmp(bs.nsym[what]);
+        CUDA_OK(c, cudaMemcpy(tmp.data(), (const u32 *)c->last.triples[what] + c->last_bd[block].ebase[what], 4ull * bs.nsym[what], cudaMemcpyDeviceToHost));
+        u64 *o = (u64 *)dst;
+        for (size_t i = 0; i < tmp.size(); i++) o[i] = tr_expand32(tmp[i]);
+    } else {
+        CUDA_OK(c, cudaMemcpy(dst, c->last.triples[what] + c->last_bd[block].ebase[what], bytes, cudaMemcpyDeviceToHost));
+    }
     *got = bytes;
     return SQ_OK;
 }

@@ -28,6 +28,10 @@ SQ_HD u32 el_pos(u64 e) { return (u32)e; }
 
 // Coding triple handed from the model replay to the range coder: cum | freq<<16 | tot<<32.
 SQ_HD u64 tr_make(u32 cum, u32 freq, u32 tot) { return (u64)cum | ((u64)freq << 16) | ((u64)tot << 32); }
+// The base model's totals never exceed 253 when a base is coded (@0x421fb0), so its triples are
+// packed in 32 bits (10-bit fields): half the traffic and footprint of the largest triple array.
+SQ_HD u32 tr_make32(u32 cum, u32 freq, u32 tot) { return cum | (freq << 10) | (tot << 20); }
+SQ_HD u64 tr_expand32(u32 t) { return tr_make(t & 0x3ffu, (t >> 10) & 0x3ffu, t >> 20); }
 
 // Name-model key space (one sort key space for the four fqzcomp name models, @0x421070):
 // prefix[256] | suffix[256] | len[256] | middle[8192].
@@ -45,6 +49,7 @@ struct BlockDesc {
     u64 ebase[ST_COUNT];              // first element of this block in the element / triple arrays
     u64 ebound[ST_COUNT];             // capacity (upper bound on coded symbols) per stream
     u64 obase[ST_COUNT];              // first byte of this block's range-coder scratch per stream
+    u64 ocap[ST_COUNT];               // its capacity
     u64 sidebase, sidecap;            // side-stream scratch (Len, Dege*) of this block
     u8 *rec;                          // where the packed record goes (device)
     u64 reccap;

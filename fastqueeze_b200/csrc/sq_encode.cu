@@ -410,7 +410,7 @@ SQ_D u32 grab32(u32 *cursor, int lane) {
 // next element is fetched one step ahead and the line after next is prefetched into L1.
 __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockDesc *bd, const BlockState *bs,
                                                     const u64 *seglist, const u32 *nseg, u32 *cursor,
-                                                    u64 *triples, const u8 *snap_seq, u8 *train_out) {
+                                                    u32 *triples, const u8 *snap_seq, u8 *train_out) {
     int lane = threadIdx.x & 31;
     u32 total = *nseg;
     for (;;) {
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockD
         u32 key = el_key(e);
         u32 S0 = 3, S1 = 3, S2 = 3, S3 = 3;
         if (snap_seq) { const u8 *t = snap_seq + (u64)key * 4; S0 = t[0]; S1 = t[1]; S2 = t[2]; S3 = t[3]; }
-        u64 *out = triples + eb;
+        u32 *out = triples + eb;
         bool hn = g + 1 < end;
         u64 en = hn ? src[g + 1] : 0;
         for (;;) {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockD
             else if (sym == 1) { cum = S0; f = S1; S1 = (S1 + 1) & 0xff; }
             else if (sym == 2) { cum = S0 + S1; f = S2; S2 = (S2 + 1) & 0xff; }
             else { cum = S0 + S1 + S2; f = S3; S3 = (S3 + 1) & 0xff; }
-            if (!train_out) out[el_pos(e)] = tr_make(cum, f, tot);
+            if (!train_out) out[el_pos(e)] = tr_make32(cum, f, tot);
             if (!hn) break;
             e = en;
             g++;
@@ -458,19 +458,41 @@ __global__ void __launch_bounds__(128) k_replay_seq(const u64 *src, const BlockD
     }
 }
 
-// 3c. SIMPLE_MODEL<N> replay (encodeSymbol @0x4221fb-0x4222f1), one WARP per context.
-// The model lives in registers, blocked over the lanes: lane l holds F[l*EPL .. l*EPL+EPL) as
-// (sym, freq) pairs, so finding the coded symbol is one ballot, its cumulative frequency one
-// warp reduction, and the +8 / halve / bubble-swap updates are lane-local (plus one neighbour
-// exchange when a swap crosses a lane boundary).  Elements are fetched 32 at a time, coalesced.
+// 3c. SIMPLE_MODEL<N> replay (encodeSymbol @0x4221fb-0x4222f1), one WARP per context, 16 symbols
+// per step.  Between two bubble-swap checks (every 16th symbol of a context, @0x4222d3) the order of
+// the table is fixed and every coded symbol adds exactly 8 to its own frequency, so for the symbols
+// s_0..s_{n-1} (n <= 16) of such a batch, with k_t the table slot of s_t and (F0, C0, tot0) the
+// frequencies / exclusive prefix sums / total at the start of the batch:
+//     cum_t  = C0[k_t] + 8 * #{u < t : k_u <  k_t}
+//     freq_t = F0[k_t] + 8 * #{u < t : k_u == k_t}
+//     tot_t  = tot0 + 8 t
+// Lane t computes step t: one table lookup and 16 shuffles instead of a serial scan + update per
+// symbol.  The model lives in shared memory (order -> symbol, symbol -> slot, F, C).  A batch in which
+// TotFreq would pass 0xffe0 (the halving, @0x4222b7, about every 4096th symbol) is replayed serially.
 // keylo/keyhi select the contexts this launch handles; snap (may be null) + snapstride give the
 // packed snapshot model of key keylo + k at snap + k * snapstride.
-template <int N, int EPL>
-__global__ void __launch_bounds__(128) k_replay_warp(const u64 *src, const BlockDesc *bd, const BlockState *bs, int stream,
-                                                     const u64 *seglist, const u32 *nseg, u32 *cursor, u64 *triples,
-                                                     u32 keylo, u32 keyhi, const u8 *snap, u32 snapstride, u8 *train_out) {
-    static_assert(EPL * 32 >= N, "lanes must cover the model");
-    int lane = threadIdx.x & 31;
+template <int N>
+SQ_D u32 rb_prefix(const u32 *F, u32 *Cm, int lane) {          // C[k] = sum of F[0..k); returns the total
+    constexpr int NP = (N + 31) / 32;
+    u32 v[NP], sum = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) { int k = lane * NP + i; v[i] = k < N ? F[k] : 0; sum += v[i]; }
+    u32 inc = warp_incl_scan(sum, lane);
+    u32 run = inc - sum;
+#pragma unroll
+    for (int i = 0; i < NP; i++) { int k = lane * NP + i; if (k < N) Cm[k] = run; run += v[i]; }
+    return __shfl_sync(FULL, inc, 31);
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) k_replay_batch(const u64 *src, const BlockDesc *bd, const BlockState *bs, int stream,
+                                                      const u64 *seglist, const u32 *nseg, u32 *cursor, u64 *triples,
+                                                      u32 keylo, u32 keyhi, const u8 *snap, u32 snapstride, u8 *train_out) {
+    __shared__ u32 s_f[4][256], s_c[4][256];
+    __shared__ u8 s_pos[4][256], s_ord[4][256];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 *F = s_f[wid], *Cm = s_c[wid];
+    u8 *pos = s_pos[wid], *ord = s_ord[wid];
     u32 total = *nseg;
     for (;;) {
         u32 idx = 0;
@@ -485,108 +507,99 @@ __global__ void __launch_bounds__(128) k_replay_warp(const u64 *src, const Block
         u64 eb = bd[b].ebase[stream];
         u64 end = eb + bs[b].nsym[stream];
         u64 *out = triples + eb;
-        u32 sy[EPL], fr[EPL];
         u32 tot, bub;
+        __syncwarp();
         if (snap) {
-            const u8 *s = snap + (u64)(key - keylo) * snapstride;
-            tot = get_u32le(s); bub = get_u32le(s + 4);
-#pragma unroll
-            for (int i = 0; i < EPL; i++) {
-                int slot = lane * EPL + i;
-                const u8 *q = s + 8 + 3 * slot;
-                sy[i] = slot < N ? q[0] : 0xffffu;
-                fr[i] = slot < N ? (u32)(q[1] | (q[2] << 8)) : 0;
+            const u8 *sp = snap + (u64)(key - keylo) * snapstride;
+            tot = get_u32le(sp); bub = get_u32le(sp + 4);
+            for (int k = lane; k < N; k += 32) {
+                const u8 *q = sp + 8 + 3 * k;
+                u32 sym = q[0];
+                ord[k] = (u8)sym; pos[sym] = (u8)k; F[k] = (u32)(q[1] | (q[2] << 8));
             }
         } else {
             tot = N; bub = 0;
-#pragma unroll
-            for (int i = 0; i < EPL; i++) {
-                int slot = lane * EPL + i;
-                sy[i] = slot < N ? (u32)slot : 0xffffu;
-                fr[i] = slot < N ? 1 : 0;
-            }
+            for (int k = lane; k < N; k += 32) { ord[k] = (u8)k; pos[k] = (u8)k; F[k] = 1; }
         }
-        u64 gi = g + lane;
-        u64 e = gi < end ? src[gi] : ~(u64)0;
+        __syncwarp();
+        rb_prefix<N>(F, Cm, lane);
+        __syncwarp();
+        u64 en = (g + lane < end) ? src[g + lane] : ~(u64)0;         // lane i holds element g + i
         for (;;) {
-            bool valid = gi < end && el_key(e) == key;
+            int room = 16 - (int)(bub & 15);                         // symbols up to and including the next swap check
+            u64 gi = g + lane;
+            u64 e = en;
+            bool valid = lane < room && gi < end && el_key(e) == key;
             u32 vb = __ballot_sync(FULL, valid);
-            int cnt = (vb == FULL) ? 32 : (__ffs(~vb) - 1);
-            u64 gn = gi + 32;
-            u64 en = (cnt == 32 && gn < end) ? src[gn] : ~(u64)0;      // next group, in flight while this one is replayed
-            u32 mysym = el_sym(e);
-            u64 mytr = 0;
-            for (int j = 0; j < cnt; j++) {
-                u32 s = __shfl_sync(FULL, mysym, j);
-                int li = -1;
+            int cnt = __ffs(~vb) - 1;                                // valid lanes form a prefix; room <= 16
+            if (cnt == 0) break;
+            {                                                        // next batch's elements, in flight during this batch
+                u64 gn = g + (u64)cnt + lane;
+                en = gn < end ? src[gn] : ~(u64)0;
+            }
+            u32 s = el_sym(e);
+            if (tot + 8u * (u32)cnt <= 0xffe0u) {
+                u32 k = 0, c0 = 0, f0 = 0;
+                if (lane < cnt) { k = pos[s]; c0 = Cm[k]; f0 = F[k]; }
+                u32 lt = 0, eq = 0;
 #pragma unroll
-                for (int i = 0; i < EPL; i++) if (sy[i] == s) li = i;
-                u32 bal = __ballot_sync(FULL, li >= 0);
-                int kl = bal ? (__ffs(bal) - 1) : 31;
-                u32 T = 0, part = 0, fsel = 0;
-#pragma unroll
-                for (int i = 0; i < EPL; i++) {
-                    if (i < li) part += fr[i];
-                    if (i == li) fsel = fr[i];
-                    T += fr[i];
+                for (int u = 0; u < 16; u++) {
+                    u32 ku = __shfl_sync(FULL, k, u);
+                    bool before = u < lane && u < cnt;
+                    lt += (before && ku < k) ? 1u : 0u;
+                    eq += (before && ku == k) ? 1u : 0u;
                 }
-                u32 contrib = lane < kl ? T : (lane == kl ? part : 0);
-                u32 cum = __reduce_add_sync(FULL, contrib);
-                u32 freq = __shfl_sync(FULL, fsel, kl);
-                if (lane == j) mytr = tr_make(cum, freq, tot);
-                // update: Freq += 8, TotFreq += 8, halve when TotFreq > 0xffe0 (@0x4222b7)
-                if (lane == kl) {
-#pragma unroll
-                    for (int i = 0; i < EPL; i++) if (i == li) fr[i] += 8;
-                }
-                tot += 8;
-                if (tot > 0xffe0u) {
-                    u32 t2 = 0;
-#pragma unroll
-                    for (int i = 0; i < EPL; i++) { fr[i] -= fr[i] >> 1; t2 += fr[i]; }
-                    tot = __reduce_add_sync(FULL, t2);
-                }
-                // bubble swap with the predecessor every 16th symbol if strictly greater (@0x4222d3-0x4222f1)
-                if (((++bub) & 15) == 0) {
-                    u32 up_s = __shfl_up_sync(FULL, sy[EPL - 1], 1), up_f = __shfl_up_sync(FULL, fr[EPL - 1], 1);
-                    u32 cur_s = 0, cur_f = 0, prv_s = up_s, prv_f = up_f;
-#pragma unroll
-                    for (int i = 0; i < EPL; i++) {
-                        if (i == li) { cur_s = sy[i]; cur_f = fr[i]; }
-                        if (i + 1 == li) { prv_s = sy[i]; prv_f = fr[i]; }
+                if (lane < cnt && !train_out) out[el_pos(e)] = tr_make(c0 + 8 * lt, f0 + 8 * eq, tot + 8 * (u32)lane);
+                __syncwarp();
+                if (lane < cnt) atomicAdd(&F[k], 8u);
+                tot += 8u * (u32)cnt;
+                bub += (u32)cnt;
+                __syncwarp();
+                rb_prefix<N>(F, Cm, lane);
+                __syncwarp();
+            } else {                                                 // the halving falls inside this batch: one symbol at a time
+                for (int t = 0; t < cnt; t++) {
+                    u32 st = __shfl_sync(FULL, s, t);
+                    u32 k = pos[st];
+                    u32 c0 = Cm[k], f0 = F[k];
+                    if (lane == t && !train_out) out[el_pos(e)] = tr_make(c0, f0, tot);
+                    __syncwarp();
+                    if (lane == 0) F[k] = f0 + 8;
+                    for (int j = (int)k + 1 + lane; j < N; j += 32) Cm[j] += 8;
+                    tot += 8;
+                    __syncwarp();
+                    if (tot > 0xffe0u) {
+                        for (int j = lane; j < N; j += 32) { u32 x = F[j]; x -= x >> 1; F[j] = x; }
+                        __syncwarp();
+                        tot = rb_prefix<N>(F, Cm, lane);
+                        __syncwarp();
                     }
-                    bool dosw = (lane == kl) && (kl * EPL + li > 0) && cur_f > prv_f;
-                    u32 swb = __ballot_sync(FULL, dosw);
-                    if (swb) {                                   // uniform
-                        int lik = __shfl_sync(FULL, li, kl);
-                        u32 cs = __shfl_sync(FULL, cur_s, kl), cf = __shfl_sync(FULL, cur_f, kl);
-                        if (lik > 0) {
-                            if (lane == kl) {
-#pragma unroll
-                                for (int i = 1; i < EPL; i++) if (i == li) { sy[i] = prv_s; fr[i] = prv_f; sy[i - 1] = cur_s; fr[i - 1] = cur_f; }
-                            }
-                        } else {
-                            if (lane == kl) { sy[0] = prv_s; fr[0] = prv_f; }
-                            if (lane == kl - 1) { sy[EPL - 1] = cs; fr[EPL - 1] = cf; }
-                        }
-                    }
+                    bub++;
                 }
             }
-            if (lane < cnt && !train_out) out[el_pos(e)] = mytr;
-            if (cnt < 32) break;
-            gi = gn;
-            e = en;
-            if (gi - lane >= end) break;
+            if ((bub & 15) == 0) {                                   // bubble swap with the predecessor if strictly greater
+                u32 sl = __shfl_sync(FULL, s, cnt - 1);
+                if (lane == 0) {
+                    u32 k = pos[sl];
+                    if (k > 0 && F[k] > F[k - 1]) {
+                        u32 fk = F[k], fp = F[k - 1];
+                        u8 ok = ord[k], op = ord[k - 1];
+                        ord[k] = op; ord[k - 1] = ok; pos[op] = (u8)k; pos[ok] = (u8)(k - 1);
+                        F[k] = fp; F[k - 1] = fk;
+                        Cm[k] = Cm[k - 1] + fk;
+                    }
+                }
+                __syncwarp();
+            }
+            g += (u64)cnt;
+            if (cnt < room) break;
         }
         if (train_out) {          // SaveModelToMem @0x420c00: u32le Tot, u32le Bub, N x {u8 sym, u16le freq} in table order
             u8 *t = train_out + (u64)(key - keylo) * snapstride;
             if (lane == 0) { put_u32le(t, tot); put_u32le(t + 4, bub); }
-#pragma unroll
-            for (int i = 0; i < EPL; i++) {
-                int slot = lane * EPL + i;
-                if (slot < N) { u8 *q = t + 8 + 3 * slot; q[0] = (u8)sy[i]; q[1] = (u8)fr[i]; q[2] = (u8)(fr[i] >> 8); }
-            }
+            for (int k = lane; k < N; k += 32) { u8 *q = t + 8 + 3 * k; u32 f = F[k]; q[0] = ord[k]; q[1] = (u8)f; q[2] = (u8)(f >> 8); }
         }
+        __syncwarp();
     }
 }
 
@@ -674,19 +687,22 @@ __global__ void __launch_bounds__(64) k_rc(const BlockDesc *bd, BlockState *bs, 
         if (threadIdx.x == 0) bs[b].olen[st] = 0;
         return;
     }
-    const u64 *tr = (st == ST_SEQ ? tr_seq : st == ST_QUAL ? tr_qual : tr_name) + bd[b].ebase[st];
+    const u64 *tr = (st == ST_QUAL ? tr_qual : tr_name) + bd[b].ebase[st];
+    const u32 *tr32 = (const u32 *)tr_seq + bd[b].ebase[st];           // the base stream's triples are packed in 32 bits
+    const bool s32 = st == ST_SEQ;
     u32 n = bs[b].nsym[st];
     u32 ngroups = (n + 31) / 32;
     if (threadIdx.x == 0) { produced = 0; consumed = 0; }
     __syncthreads();
     if (warp == 1) {
         // triples are fetched three groups ahead of the one being prepared
-        u64 t0 = (u32)lane < n ? tr[lane] : 0;
-        u64 t1 = (u64)32 + lane < n ? tr[32 + lane] : 0;
-        u64 t2 = (u64)64 + lane < n ? tr[64 + lane] : 0;
+#define RC_LOAD(i) ((u64)(i) < n ? (s32 ? tr_expand32(tr32[i]) : tr[i]) : 0)
+        u64 t0 = RC_LOAD(lane);
+        u64 t1 = RC_LOAD(32 + lane);
+        u64 t2 = RC_LOAD(64 + lane);
         for (u32 g = 0; g < ngroups; g++) {
             u64 nx = (u64)(g + 3) * 32 + lane;
-            u64 t3 = nx < n ? tr[nx] : 0;
+            u64 t3 = RC_LOAD(nx);
             while (g >= consumed + RC_NBUF) { if (RC_SLEEP) __nanosleep(RC_SLEEP); }
             u64 t = t0;
             u32 tot = (u32)(t >> 32) & 0xffffu;
@@ -704,9 +720,16 @@ __global__ void __launch_bounds__(64) k_rc(const BlockDesc *bd, BlockState *bs, 
     if (lane != 0) return;
     u8 *out = obuf + bd[b].obase[st];
     u8 *op = out;
+    u8 *lim = out + bd[b].ocap[st] - 96;       // a group writes at most 65 bytes, the flush 8
     u64 low = 0;
     u32 r0 = 0xffffffffu, sh = 0;
     for (u32 g = 0; g < ngroups; g++) {
+        if (op > lim) {                        // incompressible beyond the scratch bound: give up on this block
+            bs[b].status = SQ_ERR_CAPACITY_K;
+            consumed = ngroups + RC_NBUF;      // releases the producer
+            bs[b].olen[st] = 0;
+            return;
+        }
         while (produced <= g) { }
         __threadfence_block();
         const uint4 *rp = rec[g % RC_NBUF];
@@ -1124,7 +1147,8 @@ cudaError_t sqk_sort(const EncWave &w, int stream, int keybits, u64 *a, u64 *b, 
     return cudaSuccess;
 }
 
-cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *triples, cudaStream_t st, u64 *launches) {
+cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, void *triples_, cudaStream_t st, u64 *launches) {
+    u64 *triples = (u64 *)triples_;
     if (w.maxbound[stream] == 0) return cudaSuccess;
     CK(cudaMemsetAsync(w.nseg, 0, 4 * sizeof(u32), st));
     dim3 g(cdiv(w.maxbound[stream], 256), w.B);
@@ -1132,16 +1156,16 @@ cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *tri
     *launches += 1;
     int nsm = w.nsm;
     if (stream == ST_SEQ) {
-        k_replay_seq<<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, triples, w.snap_seq, w.train_seq);
+        k_replay_seq<<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, (u32 *)triples_, w.snap_seq, w.train_seq);
         *launches += 1;
     } else if (stream == ST_QUAL) {
-        k_replay_warp<95, 3><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1, triples,
+        k_replay_batch<95><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1, triples,
                                                     0, 1u << 24, w.snap_qual, 293, w.train_qual);
         *launches += 1;
     } else {
-        k_replay_warp<256, 8><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1,
+        k_replay_batch<256><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1,
                                                      triples, 0, NK_MIDDLE, w.snap_name, 776, w.train_name);
-        k_replay_warp<128, 4><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 2,
+        k_replay_batch<128><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 2,
                                                      triples, NK_MIDDLE, NK_TOTAL,
                                                      w.snap_name ? w.snap_name + 3ull * 256 * 776 : nullptr, 392,
                                                      w.train_name ? w.train_name + 3ull * 256 * 776 : nullptr);

@@ -30,7 +30,7 @@ struct EncWave {
     // per symbol
     u64 maxbound[ST_COUNT];     // max over blocks of ebound (grid sizing)
     u64 *elemA, *elemB;
-    u64 *triples[ST_COUNT];
+    u64 *triples[ST_COUNT];     // [ST_SEQ] really holds u32 (tr_make32)
     u32 *hist;
     u64 *seglist; u32 segcap; u32 *nseg;   // nseg[0] count, nseg[1..2] work cursors
     u8 *obuf;                   // range-coder scratch
@@ -46,7 +46,7 @@ cudaError_t sqk_rblock(const EncWave &w, double r, cudaStream_t st, u64 *launche
 cudaError_t sqk_count(const EncWave &w, cudaStream_t st, u64 *launches);
 cudaError_t sqk_emit(const EncWave &w, int stream, u64 *elem, cudaStream_t st, u64 *launches);
 cudaError_t sqk_sort(const EncWave &w, int stream, int keybits, u64 *a, u64 *b, u64 **sorted, cudaStream_t st, u64 *launches);
-cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, u64 *triples, cudaStream_t st, u64 *launches);
+cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, void *triples, cudaStream_t st, u64 *launches);
 cudaError_t sqk_rc(const EncWave &w, int stream, cudaStream_t st, u64 *launches);
 cudaError_t sqk_md5(const EncWave &w, cudaStream_t st, u64 *launches);
 cudaError_t sqk_side(const EncWave &w, cudaStream_t st, u64 *launches);
