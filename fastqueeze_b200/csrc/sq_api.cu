@@ -206,7 +206,7 @@ BlkCost block_cost(const sq_ctx *c, const sq_block_in &b, bool host) {
     k.eb[ST_NAME] = c->p.id_rule ? 0 : b.idbytes + 3 * n;
     k.obuf = 0;
     for (int s = 0; s < ST_COUNT; s++) k.obuf += al16(k.eb[s] + k.eb[s] / 2 + 256);
-    k.side = al16(16 * n + b.seqbytes / 2 + 4096);
+    k.side = al16(24 * n + b.seqbytes + 4096);
     k.rec = al16(256 + b.idbytes + 2 * b.seqbytes + 8 * n);
     return k;
 }

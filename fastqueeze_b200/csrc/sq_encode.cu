@@ -837,11 +837,13 @@ __global__ void __launch_bounds__(160) k_side(const BlockDesc *bd, BlockState *b
     u32 nch = (u32)d.seqbytes - bs[b].acgt;
     u32 nf = bs[b].side_cnt[3];
     if (threadIdx.x == 0) {
-        // scratch regions: Len, Tip, Ch, MaxQ, Cnt, Pos (generous; overflow is detected, not assumed away)
+        // scratch regions: Len, Tip, Ch, MaxQ, Cnt, Pos.  Len / Tip / MaxQ get their worst case (2 B per
+        // symbol); Ch gets 1 B per non-ACGT base (an 11-symbol alphabet needs < 0.5 B), Pos the rest
+        // (>= 1 B per candidate base).  Overflow is detected by the coder, never assumed away.
         u64 o = 0;
         sm.off[0] = o; o += 6ull * n + 16;
         sm.off[1] = o; o += 2ull * n + 16;
-        sm.off[2] = o; o += 2ull * nch + 16;
+        sm.off[2] = o; o += (u64)nch + 64;
         sm.off[3] = o; o += 2ull * nf + 16;
         sm.off[4] = o; o += 8ull * nf + 16;
         sm.off[5] = o;
@@ -1047,7 +1049,7 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDesc *bd, const BlockSt
         u64 o = 6ull * d.nreads + 16;                              // region offsets as laid out by k_side
         u32 nch = (u32)d.seqbytes - s.acgt, nf = s.side_cnt[3];
         u64 offs[6] = {0, o, o + 2ull * d.nreads + 16, 0, 0, 0};
-        offs[3] = offs[2] + 2ull * nch + 16;
+        offs[3] = offs[2] + (u64)nch + 64;
         offs[4] = offs[3] + 2ull * nf + 16;
         offs[5] = offs[4] + 8ull * nf + 16;
         for (int k = 1; k < 6; k++) {
