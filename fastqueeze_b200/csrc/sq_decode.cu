@@ -21,12 +21,11 @@
 // the decoding warp, EPL consecutive entries per lane (lane l owns F[l*EPL .. l*EPL+EPL)):
 //   row i   (i < EPL), word l : entry i of lane l = sym | bub << 8 (row 0 only) | freq << 16
 //   row EPL,           word l : base_l | tot << 16, base_l = sum of the frequencies of all lower lanes
-//   row EPL+1,         word l : reciprocal estimate of tot, so that range / tot is one multiply + fix-ups
 // Every word is only ever read and written by its own lane, every row is one coalesced 128-byte
 // access, and a symbol is found with EPL multiply-compares per lane + one ballot (no second division:
 // target = code / r  is replaced by comparing code with cum * r, which is the same test on integers).
 template <int N, int EPL> struct WM {
-    static constexpr int ROWS = EPL + 2;
+    static constexpr int ROWS = EPL + 1;
     static constexpr int STRIDE = ROWS * 32;          // words per model
 };
 #define WQ_STRIDE (WM<95, 3>::STRIDE)
@@ -144,7 +143,6 @@ __global__ void __launch_bounds__(256) k_init_wm(DecBlock *db, int which, u32 nm
 #pragma unroll
         for (int i = 0; i < EPL; i++) mp[i * 32 + lane] = w[i];
         mp[EPL * 32 + lane] = base | (tot << 16);
-        mp[(EPL + 1) * 32 + lane] = recip_est(tot < 2 ? 2 : tot);
     }
 }
 __global__ void k_init_seqtab(DecBlock *db, u64 bytes, const u8 *snap) {
@@ -159,21 +157,20 @@ __global__ void k_init_seqtab(DecBlock *db, u64 bytes, const u8 *snap) {
 
 // decodeSymbol (inlined e.g. @0x42a7d0-0x42a960) on a warp model, in three phases so that the
 // caller can issue the NEXT model's loads between the search and the write-back of this one.
-template <int EPL> struct WReg { u32 w[EPL]; u32 bt, m32; };
+template <int EPL> struct WReg { u32 w[EPL]; u32 bt; };
 
 template <int EPL>
 SQ_D void wm_load(WReg<EPL> &R, const u32 *mp, int lane) {
 #pragma unroll
     for (int i = 0; i < EPL; i++) R.w[i] = mp[i * 32 + lane];
     R.bt = mp[EPL * 32 + lane];
-    R.m32 = mp[(EPL + 1) * 32 + lane];
 }
 
 // search + coder step; rc is warp-uniform.  Returns the symbol on every lane; kl / li locate it.
 template <int N, int EPL>
 SQ_D u32 wm_search(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li) {
     u32 base = R.bt & 0xffffu, tot = R.bt >> 16;
-    u32 q = div_est(rc.range, tot, R.m32);
+    u32 q = div_est(rc.range, tot, recip_est(tot));
     rc.range = q;
     u32 code = rc.code;
     li = -1;
@@ -246,11 +243,9 @@ SQ_D void wm_update_store(u32 *mp, WReg<EPL> &R, int kl, int li, int lane) {
     }
     R.w[0] |= bub << 8;
     R.bt = base | (tot << 16);
-    R.m32 = recip_est(tot);
-    // row 0 carries bub, the base row tot, the last row its reciprocal: rewritten by every lane
+    // row 0 carries bub and the base row tot: both are rewritten by every lane
     mp[lane] = R.w[0];
     mp[EPL * 32 + lane] = R.bt;
-    mp[(EPL + 1) * 32 + lane] = R.m32;
     if (mine || prevlane || all) {
 #pragma unroll
         for (int i = 1; i < EPL; i++) mp[i * 32 + lane] = R.w[i];

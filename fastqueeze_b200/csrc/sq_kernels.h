@@ -55,9 +55,9 @@ cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launch
 
 // ---------------------------------------------------------------------------------------------
 // decode side (sq_decode.cu)
-// decoder-private "warp model" tables: (EPL + 2) rows of 32 words per model
-#define SQ_WQ_STRIDE (5 * 32)                                  /* SIMPLE_MODEL<95>, 3 entries per lane */
-#define SQ_WNAME_WORDS (768ull * 10 * 32 + 8192ull * 6 * 32)     /* 768 x <256> (8 per lane) + 8192 x <128> (4 per lane) */
+// decoder-private "warp model" tables: (EPL + 1) rows of 32 words per model
+#define SQ_WQ_STRIDE (4 * 32)                                  /* SIMPLE_MODEL<95>, 3 entries per lane */
+#define SQ_WNAME_WORDS (768ull * 9 * 32 + 8192ull * 5 * 32)     /* 768 x <256> (8 per lane) + 8192 x <128> (4 per lane) */
 struct DecBlock {
     const u8 *rec; u64 reclen;          // block record (device)
     // payload pointers / sizes of the streams found in the record (0 = absent); MD5 prefixes skipped
