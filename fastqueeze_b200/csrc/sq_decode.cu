@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
     const u32 *seqoff = d.seqoff;
     const i32 *seqlen = d.seqlen;
     if (wid == 0) {                                            // names (decompressName @0x428ca0)
-        if (id_rule) { if (lane == 0) d.status = SQ_ERR_FORMAT_K; return; }   // rule-based IDs: regenerated on the host ("next" row)
+        if (id_rule) { if (lane == 0) d.idbytes = 0; return; }   // rule-based IDs (IDProcess::decodeIDS) are regenerated by the host layer from the tag-5 payload
         for (int i = lane; i < 1024; i += 32) sm.ns.last[i] = ' ';
         __syncwarp();
         int lnl = 0, lpl = 0, lsl = 0;
@@ -611,10 +611,11 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
 }
 
 // blockMd5Verify @0x414e00 ("Name/Seq/Qual md5 unequal", .rodata+0x15bc)
-__global__ void __launch_bounds__(32) k_dec_md5(DecBlock *db, int B) {
+__global__ void __launch_bounds__(32) k_dec_md5(DecBlock *db, int B, int id_rule) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 3 * B) return;
     int b = t / 3, which = t % 3;
+    if (which == 0 && id_rule) return;           // names are regenerated (and checked) on the host in this mode
     DecBlock &d = db[b];
     if (d.status != 0 || !d.has_md5[which]) return;
     const u8 *p = which == 0 ? d.ids : which == 1 ? d.seq : d.qual;
@@ -647,6 +648,6 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
     else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
     else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
     *launches += 2;
-    if (w.md5) { k_dec_md5<<<cdivd(3ull * B, 32), 32, 0, st>>>(w.db, B); *launches += 1; }
+    if (w.md5) { k_dec_md5<<<cdivd(3ull * B, 32), 32, 0, st>>>(w.db, B, w.id_rule); *launches += 1; }
     return cudaGetLastError();
 }

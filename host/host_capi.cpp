@@ -5,6 +5,7 @@
 
 #include "arc_file.h"
 #include "fastq_block.h"
+#include "id_process.h"
 
 using namespace sqhost;
 
@@ -48,6 +49,50 @@ int sqh_write_arc(const char *path, int pe, int usemodel, int lossy, int md5, co
     if (idbin) memcpy(p.idbin, idbin, 512);
     if (model) p.model.assign(model, model + modellen);
     return w.finish(p) ? 0 : -1;
+}
+
+// SeqArcPreProcess's ID-bin analysis over the head sample blocks of the input (sample blocks: whole records until
+// BlockSize (SE) / BlockSize/2 per mate (PE) bytes, at most five).  Fills idbin[512]; returns idbin[0].
+int sqh_analyse_ids(const char *p1, const char *p2, uint64_t block_bytes, uint8_t *idbin) {
+    try {
+        bool pe = p2 && *p2;
+        FILE *f1 = fopen(p1, "rb"), *f2 = pe ? fopen(p2, "rb") : nullptr;
+        if (!f1 || (pe && !f2)) return -1;
+        uint64_t quota = block_bytes / (pe ? 2 : 1);
+        char *line = nullptr;
+        size_t cap = 0;
+        auto record = [&](FILE *f, std::vector<char> &t) {
+            for (int k = 0; k < 4; k++) { ssize_t n = getline(&line, &cap, f); if (n <= 0) return false; t.insert(t.end(), line, line + n); }
+            return true;
+        };
+        memset(idbin, 0, 512);
+        bool ok = true;
+        for (int b = 0; b < 5 && ok; b++) {
+            std::vector<char> t1, t2;
+            while (t1.size() < quota) { if (!record(f1, t1)) break; if (pe && !record(f2, t2)) break; }
+            if (t1.empty()) break;
+            MemBuf mb;
+            parse_block(t1, t2, pe, mb);
+            ok = analyse_id_bins(mb, pe, idbin);
+        }
+        free(line);
+        fclose(f1);
+        if (f2) fclose(f2);
+        return idbin[0];
+    } catch (const std::exception &) {
+        return -2;
+    }
+}
+
+// IDProcess::decodeIDS on one tag-5 payload; returns the number of ID bytes written (<= cap) or -1.
+long sqh_decode_ids(const uint8_t *payload, uint64_t paylen, const uint8_t *idbin, const int32_t *seqlen, uint32_t nreads,
+                    uint8_t *ids, uint64_t cap, uint16_t *idlen) {
+    std::vector<uint8_t> o;
+    std::vector<uint16_t> l;
+    if (!decode_ids(payload, paylen, idbin, seqlen, nreads, o, l) || o.size() > cap || l.size() != nreads) return -1;
+    memcpy(ids, o.data(), o.size());
+    memcpy(idlen, l.data(), 2 * l.size());
+    return (long)o.size();
 }
 
 // Parse an archive; returns the number of blocks and fills flags = pe | usemodel<<1 | lossy<<2 | md5<<3 | idrule<<4.

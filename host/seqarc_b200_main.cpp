@@ -18,6 +18,7 @@
 #include "../include/seqarc_b200.h"
 #include "arc_file.h"
 #include "fastq_block.h"
+#include "id_process.h"
 
 using namespace sqhost;
 
@@ -122,12 +123,16 @@ static int do_compress(const Opt &o) {
     ArcParams ap;
     ap.pe = pe; ap.usemodel = usemodel; ap.lossy = o.lossy; ap.md5 = o.md5;
     ap.name1 = base_name(o.in1); ap.name2 = base_name(o.in2);
-    // ID-bin analysis (IDProcess::analysisIDBinType @0x4310a0) is not restated: IDs always take the
-    // name-model path (idbin all zero), which every SeqArc decoder reads.
-    sq_ctx *c = make_ctx(o, usemodel, o.lossy, o.lossy_r, o.md5, 0);
+    // SeqArcPreProcess::doPreProcess @0x4153b0: the ID-bin analysis runs over the head sample blocks and stops
+    // at the first block whose IDs are not rule-predictable; the same blocks train the snapshot when usemodel
+    std::vector<MemBuf> sample;
+    sample_blocks(o, sample);
+    bool okbins = true;
+    for (auto &m : sample)
+        if (okbins) okbins = analyse_id_bins(m, pe, ap.idbin);
+    if (o.verbose) fprintf(stderr, "bOrderBin %d petype %d\n", ap.idbin[0], ap.idbin[1]);
+    sq_ctx *c = make_ctx(o, usemodel, o.lossy, o.lossy_r, o.md5, ap.idbin[0]);
     if (usemodel) {
-        std::vector<MemBuf> sample;
-        sample_blocks(o, sample);
         std::vector<sq_block_in> in;
         for (auto &m : sample) in.push_back(as_in(m));
         ap.model.resize(sq_model_size(c));
@@ -177,14 +182,45 @@ static int do_compress(const Opt &o) {
     return 0;
 }
 
+// tag-5 payload of a block record: [16-byte MD5] + u16le length + first ID (compressID @0x4247c0)
+static bool find_id_payload(const uint8_t *rec, uint64_t len, bool md5, const uint8_t **pay, size_t *plen, const uint8_t **dig) {
+    auto vint = [](const uint8_t *p, const uint8_t *end, uint64_t *v) {
+        if (p >= end) return 0;
+        int n = 1;
+        uint8_t m = 0x80;
+        while (n <= 8 && !(p[0] & m)) { n++; m >>= 1; }
+        if (n > 8 || p + n > end) return 0;
+        uint64_t x = p[0] & (m - 1);
+        for (int i = 1; i < n; i++) x = (x << 8) | p[i];
+        *v = x;
+        return n;
+    };
+    const uint8_t *p = rec, *end = rec + len;
+    uint64_t tag, sz;
+    int k = vint(p, end, &tag); if (!k) return false; p += k;
+    k = vint(p, end, &sz); if (!k) return false; p += k;
+    while (p < end) {
+        k = vint(p, end, &tag); if (!k) return false; p += k;
+        k = vint(p, end, &sz); if (!k || p + sz > end) return false; p += k;
+        if (tag == 5) {
+            *dig = nullptr;
+            if (md5) { if (sz < 16) return false; *dig = p; p += 16; sz -= 16; }
+            *pay = p; *plen = sz;
+            return true;
+        }
+        p += sz;
+    }
+    return false;
+}
+
 static int do_decompress(const Opt &o) {
     ArcReader ar;
     if (!ar.load(o.arc)) die(ar.err);
-    if (ar.p.idbin[0]) die("archive uses the rule-based ID path (IDProcess::decodeIDS), which is not implemented yet");
+    const bool rule = ar.p.idbin[0] != 0;
     bool pe = ar.p.pe;
     std::string n1 = pe ? o.out + "_1.fastq" : o.out + ".fastq", n2 = o.out + "_2.fastq";
     if (!o.force && (exists(n1) || (pe && exists(n2)))) die("output exists (use -f)");
-    sq_ctx *c = make_ctx(o, ar.p.usemodel, ar.p.lossy, 1.5, ar.p.md5, 0);
+    sq_ctx *c = make_ctx(o, ar.p.usemodel, ar.p.lossy, 1.5, ar.p.md5, rule);
     if (ar.p.usemodel && sq_load_model(c, ar.p.model.data(), ar.p.model.size()) != SQ_OK) die(sq_last_error(c));
     FILE *f1 = fopen(n1.c_str(), "wb"), *f2 = pe ? fopen(n2.c_str(), "wb") : nullptr;
     if (!f1 || (pe && !f2)) die("cannot create output");
@@ -215,6 +251,18 @@ static int do_decompress(const Opt &o) {
         for (int i = 0; i < n; i++) {
             MemBuf &m = mbs[i];
             m.idlen.resize(dec[i].nreads); m.seqlen.resize(dec[i].nreads);
+            if (rule) {               // IDProcess::decodeIDS @0x430610: regenerate the IDs from the block's first ID
+                const uint8_t *pay = nullptr, *md5 = nullptr;
+                size_t plen = 0;
+                if (!find_id_payload(recs[i], lens[i], ar.p.md5, &pay, &plen, &md5)) die("decode: block without an ID stream");
+                m.ids.clear(); m.idlen.clear();
+                if (!decode_ids(pay, plen, ar.p.idbin, m.seqlen.data(), dec[i].nreads, m.ids, m.idlen)) die("decode: bad rule-based ID record");
+                if (md5) {
+                    uint8_t dig[16];
+                    md5_digest(m.ids.data(), m.ids.size(), dig);
+                    if (memcmp(dig, md5, 16) != 0) die("decode: Name md5 unequal");
+                }
+            }
             render_block(m, pe, o1, o2);
             fwrite(o1.data(), 1, o1.size(), f1);
             if (pe) fwrite(o2.data(), 1, o2.size(), f2);

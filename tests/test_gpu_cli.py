@@ -15,8 +15,8 @@ from oracle import pyoracle as po
 pytestmark = pytest.mark.gpu
 CLI = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
 
-# archives whose IDs the reference codes with the name model (idbin all zero): byte identity expected
-IDENTICAL = ["illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
+# every golden archive, rule-predictable IDs (ERR / SRR style) included: byte identity expected
+IDENTICAL = ["err_pe1000", "err_pe1000_nomd5", "srr_pe100", "illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
              "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel", "illumina_pe150_usemodel"]
 
 
@@ -58,9 +58,6 @@ def test_cli_archive_is_byte_identical_to_reference(name):
 
 @pytest.mark.parametrize("name", [c for c in common.CASES if "lossy" not in c])
 def test_cli_decodes_reference_archive(name):
-    kw, _ = common.case_params(name)
-    if kw["id_rule"]:
-        pytest.skip("rule-based ID regeneration (IDProcess::decodeIDS) is a 'next' row")
     with tempfile.TemporaryDirectory() as d:
         m, fq, paths = _setup(name, d)
         open(os.path.join(d, "ref.arc"), "wb").write(common.case_archive(name))

@@ -87,3 +87,75 @@ def test_arc_writer_reproduces_reference_file(hl, name):
         assert r == 0
         got = open(out, "rb").read()
     assert got == data
+
+
+def _hl_ids(hl):
+    hl.sqh_analyse_ids.restype = C.c_int
+    hl.sqh_analyse_ids.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_void_p]
+    hl.sqh_decode_ids.restype = C.c_long
+    hl.sqh_decode_ids.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    return hl
+
+
+@pytest.mark.parametrize("name", common.CASES)
+def test_id_bin_analysis_matches_reference_trailer(hl, name):
+    """IDProcess::analysisIDBinType over the pre-process sample blocks gives the 512-byte array the reference stored."""
+    _hl_ids(hl)
+    m = common.MANIFEST[name]
+    arc = arcwalk.parse_arc(common.case_archive(name))
+    want = arc["trailer"]["params"][15]
+    bs = int((m["config"] or {}).get("BlockSize(M)", 50)) << 20
+    with tempfile.TemporaryDirectory() as d:
+        paths = _write_inputs(name, d)
+        idbin = np.zeros(512, np.uint8)
+        r = hl.sqh_analyse_ids(paths[0].encode(), paths[1].encode() if m["pe"] else None, bs, idbin.ctypes.data)
+    assert r == want[0]
+    assert idbin.tobytes() == want
+
+
+@pytest.mark.parametrize("name", ["err_pe1000", "err_pe1000_nomd5", "srr_pe100"])
+def test_rule_based_ids_are_regenerated(hl, name):
+    """IDProcess::decodeIDS: every ID of the block from the stored first ID + the ID-bin array."""
+    _hl_ids(hl)
+    kw, blocks = common.case_blocks(name)
+    arc = arcwalk.parse_arc(common.case_archive(name))
+    idbin = np.frombuffer(arc["trailer"]["params"][15], np.uint8).copy()
+    assert kw["id_rule"] == 1
+    for (blk, ref), ab in zip(blocks, arc["blocks"]):
+        pay = ab["streams"][5][16 if kw["md5"] else 0:]
+        pa = np.frombuffer(pay, np.uint8)
+        ids = np.zeros(blk.ids.shape[0] + 64, np.uint8)
+        idlen = np.zeros(blk.nreads, np.uint16)
+        sl = np.ascontiguousarray(blk.seqlen)
+        n = hl.sqh_decode_ids(pa.ctypes.data, len(pay), idbin.ctypes.data, sl.ctypes.data, blk.nreads, ids.ctypes.data,
+                              ids.shape[0], idlen.ctypes.data)
+        assert n == blk.ids.shape[0]
+        assert ids[:n].tobytes() == blk.ids.tobytes()
+        assert np.array_equal(idlen, blk.idlen)
+
+
+def test_id_bin_analysis_on_other_id_styles(hl):
+    """Styles the reference was observed on plus the edge rules read from the disassembly."""
+    _hl_ids(hl)
+    import numpy as np
+
+    def run(ids1, ids2=None, L=50):
+        with tempfile.TemporaryDirectory() as d:
+            ps = []
+            for k, ids in enumerate([ids1] + ([ids2] if ids2 else [])):
+                p = os.path.join(d, "x_%d.fq" % k)
+                with open(p, "wb") as f:
+                    for s in ids:
+                        f.write(b"@" + s + b"\n" + b"A" * L + b"\n+\n" + b"I" * L + b"\n")
+                ps.append(p)
+            idbin = np.zeros(512, np.uint8)
+            r = hl.sqh_analyse_ids(ps[0].encode(), ps[1].encode() if ids2 else None, 1 << 20, idbin.ctypes.data)
+            return r, bytes(idbin[:8])
+    assert run([b"read%d" % i for i in range(1, 50)])[0] == 0                    # "read1": one token, not all digits
+    r, b = run([b"r.%d" % i for i in range(1, 50)])
+    assert r == 1 and b[:4] == bytes([1, 0, 0, 1])                               # constant + counter, single-end
+    r, b = run([b"r.%d/1" % i for i in range(1, 50)], [b"r.%d/2" % i for i in range(1, 50)])
+    assert r == 1 and b[:5] == bytes([1, 2, 0, 1, 0])                            # petype 2: .../1 vs .../2
+    assert run([b"r.%d" % (2 * i) for i in range(1, 50)])[0] == 0                # step 2 is not a rule
+    r, b = run([b"r.%d len=50" % i for i in range(1, 50)])
+    assert r == 1 and b[:6] == bytes([1, 0, 0, 1, 0, 3])                         # "len" token + read length
