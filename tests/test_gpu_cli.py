@@ -80,3 +80,30 @@ def test_reference_decodes_cli_archive(name):
         outs = ["back_1.fastq", "back_2.fastq"] if m["pe"] else ["back.fastq"]
         for o, t in zip(outs, fq):
             assert open(os.path.join(d, o), "rb").read() == t
+
+
+def test_config1_reference_test_pair_matches_survey_md5():
+    """BASELINE configs[0]: the reference's own test/ERR2755197_test_{1,2}.fq (committed gzipped; 10,000 pairs, rule-predictable
+    IDs).  SURVEY section 4 recorded what SeqArc-1.6 -c -t 1 writes for it: 821,500 bytes, md5 c8ba98391ac4607d9559db23875152ba,
+    and under the newline-guard shim with -l 1.15: 224,143 bytes, md5 e21845c348c28dbe7cb54c9d627869e2."""
+    import gzip
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        texts = []
+        for k in (1, 2):
+            t = gzip.open(os.path.join(common.GOLD, "ERR2755197_test_%d.fq.gz" % k), "rb").read()
+            p = os.path.join(d, "ERR2755197_test_%d.fq" % k)
+            open(p, "wb").write(t)
+            paths.append(p)
+            texts.append(t)
+        for extra, size, md5 in (([], 821500, "c8ba98391ac4607d9559db23875152ba"), (["-l", "1.15"], 224143, "e21845c348c28dbe7cb54c9d627869e2")):
+            r = subprocess.run([CLI, "-c", "-f", "-1", paths[0], "-2", paths[1], "-o", "pe"] + extra, cwd=d, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr
+            arc = open(os.path.join(d, "pe.arc"), "rb").read()
+            assert len(arc) == size
+            assert hashlib.md5(arc).hexdigest() == md5
+            if not extra:
+                r = subprocess.run([CLI, "-d", "-f", "pe.arc", "-o", "back"], cwd=d, capture_output=True, text=True, timeout=600)
+                assert r.returncode == 0, r.stderr
+                assert open(os.path.join(d, "back_1.fastq"), "rb").read() == texts[0]
+                assert open(os.path.join(d, "back_2.fastq"), "rb").read() == texts[1]
