@@ -228,7 +228,7 @@ struct WaveAcc {
         }
         t += 16 * me + 512;                                   // elemA + elemB
         t += 8 * ms + 256;                                    // seglist
-        t += (u64)B * (1u << SQ_SORT_BITS) * mt * 4 + 256;    // hist
+        t += (u64)B * (1u << SQ_SORT_BITS_WIDE) * mt * 4 + 256;    // hist
         t += (u64)B * (sizeof(BlockDesc) + sizeof(BlockState) + 6 * 4 + 8 + 4) + 2048;
         (void)c;
         return t;
@@ -313,7 +313,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     for (int s = 0; s < ST_COUNT; s++) w.triples[s] = (u64 *)need(A.take((s == ST_SEQ ? 4 : 8) * (sum[s] + 2)));
     u64 maxtiles = 0;
     for (int s = 0; s < ST_COUNT; s++) maxtiles = std::max(maxtiles, (w.maxbound[s] + SQ_TILE - 1) / SQ_TILE);
-    w.hist = (u32 *)need(take<u32>(A, (u64)n * (1u << SQ_SORT_BITS) * maxtiles + 1));
+    w.hist = (u32 *)need(take<u32>(A, (u64)n * (1u << SQ_SORT_BITS_WIDE) * maxtiles + 1));
     u64 segcap = std::max(segsum[0], std::max(segsum[1], segsum[2])) + 1;
     if (segcap > 0xffffffffull) { c->err = "segment list too large"; return SQ_ERR_ARG; }
     w.segcap = (u32)segcap;

@@ -159,16 +159,32 @@ __global__ void k_init_seqtab(DecBlock *db, u64 bytes, const u8 *snap) {
 // caller can issue the NEXT model's loads between the search and the write-back of this one.
 template <int EPL> struct WReg { u32 w[EPL]; u32 bt; };
 
+// L2 residency hints.  The warp-model tables (hot set: a few hundred KB per block) must survive in L2
+// beside the base-context tables, whose accesses are uniformly random over 4 MB per block and would
+// otherwise evict them: models are accessed evict_last, base-context sectors evict_first.
+SQ_D u64 l2_policy_keep() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+SQ_D u64 l2_policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+SQ_D u32 ld_hint(const u32 *p, u64 pol) {
+    u32 v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+SQ_D void st_hint(u32 *p, u32 v, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 template <int EPL>
-SQ_D void wm_load(WReg<EPL> &R, const u32 *mp, int lane) {
+SQ_D void wm_load(WReg<EPL> &R, const u32 *mp, int lane, u64 pol) {
 #pragma unroll
-    for (int i = 0; i < EPL; i++) R.w[i] = mp[i * 32 + lane];
-    R.bt = mp[EPL * 32 + lane];
+    for (int i = 0; i < EPL; i++) R.w[i] = ld_hint(mp + i * 32 + lane, pol);
+    R.bt = ld_hint(mp + EPL * 32 + lane, pol);
 }
 
 // search + coder step; rc is warp-uniform.  Returns the symbol on every lane; kl / li locate it.
+// wm_find leaves the coder step (rc.decode(cex, freq)) to the caller, which can then request the
+// next model -- it only depends on the symbol -- before renormalising.
 template <int N, int EPL>
-SQ_D u32 wm_search(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li) {
+SQ_D u32 wm_find(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li, u32 &cex_out, u32 &freq_out) {
     u32 base = R.bt & 0xffffu, tot = R.bt >> 16;
     u32 q = div_est(rc.range, tot, recip_est(tot));
     rc.range = q;
@@ -191,14 +207,22 @@ SQ_D u32 wm_search(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li) {
     kl = bal ? (__ffs(bal) - 1) : (N - 1) / EPL;
     wsel = __shfl_sync(FULL, wsel, kl);
     cex = __shfl_sync(FULL, cex, kl);
-    rc.decode(cex, wsel >> 16);
+    cex_out = cex;
+    freq_out = wsel >> 16;
     return wsel & 0xff;
+}
+template <int N, int EPL>
+SQ_D u32 wm_search(const WReg<EPL> &R, RcDecW &rc, int lane, int &kl, int &li) {
+    u32 cex, freq;
+    u32 sym = wm_find<N, EPL>(R, rc, lane, kl, li, cex, freq);
+    rc.decode(cex, freq);
+    return sym;
 }
 
 // model update (Freq += 8, TotFreq += 8, halve above 0xffe0, bubble swap every 16th symbol) and
 // write-back; R is left holding the updated model.
 template <int N, int EPL>
-SQ_D void wm_update_store(u32 *mp, WReg<EPL> &R, int kl, int li, int lane) {
+SQ_D void wm_update_store(u32 *mp, WReg<EPL> &R, int kl, int li, int lane, u64 pol) {
     u32 base = R.bt & 0xffffu, tot = R.bt >> 16;
     u32 bub = (R.w[0] >> 8) & 0xff;
     R.w[0] &= 0xffff00ffu;
@@ -244,21 +268,21 @@ SQ_D void wm_update_store(u32 *mp, WReg<EPL> &R, int kl, int li, int lane) {
     R.w[0] |= bub << 8;
     R.bt = base | (tot << 16);
     // row 0 carries bub and the base row tot: both are rewritten by every lane
-    mp[lane] = R.w[0];
-    mp[EPL * 32 + lane] = R.bt;
+    st_hint(mp + lane, R.w[0], pol);
+    st_hint(mp + EPL * 32 + lane, R.bt, pol);
     if (mine || prevlane || all) {
 #pragma unroll
-        for (int i = 1; i < EPL; i++) mp[i * 32 + lane] = R.w[i];
+        for (int i = 1; i < EPL; i++) st_hint(mp + i * 32 + lane, R.w[i], pol);
     }
 }
 
 template <int N, int EPL>
-SQ_D u32 wm_decode(u32 *mp, RcDecW &rc, int lane) {
+SQ_D u32 wm_decode(u32 *mp, RcDecW &rc, int lane, u64 pol) {
     WReg<EPL> R;
-    wm_load(R, mp, lane);
+    wm_load(R, mp, lane, pol);
     int kl, li;
     u32 sym = wm_search<N, EPL>(R, rc, lane, kl, li);
-    wm_update_store<N, EPL>(mp, R, kl, li, lane);
+    wm_update_store<N, EPL>(mp, R, kl, li, lane, pol);
     return sym;
 }
 
@@ -297,17 +321,17 @@ __global__ void __launch_bounds__(32) k_dec_len(DecBlock *db) {
 // are warp models, last_name / the name being built live in shared memory.
 struct NameSmem { u8 last[1024]; u8 cur[256]; };
 
-SQ_D int decode_name(u32 *nametab, RcDecW &rc, u8 *name_out, u64 room, NameSmem &ns, int &lnl, int &lpl, int &lsl, int lane) {
+SQ_D int decode_name(u32 *nametab, RcDecW &rc, u8 *name_out, u64 room, NameSmem &ns, int &lnl, int &lpl, int &lsl, int lane, u64 pol) {
     u32 *prefix = nametab, *suffix = prefix + 256 * W256_STRIDE, *lenm = suffix + 256 * W256_STRIDE;
     u32 *middle = lenm + 256 * W256_STRIDE;
     // the three header models of a read are known up front: fetch them together
     WReg<8> Rp, Rs, Rl;
     u32 *mpp = prefix + (u64)lpl * W256_STRIDE, *mps = suffix + (u64)lsl * W256_STRIDE, *mpl = lenm + (u64)lnl * W256_STRIDE;
-    wm_load(Rp, mpp, lane); wm_load(Rs, mps, lane); wm_load(Rl, mpl, lane);
+    wm_load(Rp, mpp, lane, pol); wm_load(Rs, mps, lane, pol); wm_load(Rl, mpl, lane, pol);
     int kl, li;
-    int p = (int)wm_search<256, 8>(Rp, rc, lane, kl, li); wm_update_store<256, 8>(mpp, Rp, kl, li, lane);
-    int s = (int)wm_search<256, 8>(Rs, rc, lane, kl, li); wm_update_store<256, 8>(mps, Rs, kl, li, lane);
-    int n = (int)wm_search<256, 8>(Rl, rc, lane, kl, li); wm_update_store<256, 8>(mpl, Rl, kl, li, lane);
+    int p = (int)wm_search<256, 8>(Rp, rc, lane, kl, li); wm_update_store<256, 8>(mpp, Rp, kl, li, lane, pol);
+    int s = (int)wm_search<256, 8>(Rs, rc, lane, kl, li); wm_update_store<256, 8>(mps, Rs, kl, li, lane, pol);
+    int n = (int)wm_search<256, 8>(Rl, rc, lane, kl, li); wm_update_store<256, 8>(mpl, Rl, kl, li, lane, pol);
     lpl = p; lsl = s;
     if ((u64)n > room) return -1;                                          // caller's ID buffer is full
     if (p > n || s > n - p || s > lnl) { p = p > n ? n : p; s = 0; }       // corrupt stream guard
@@ -319,7 +343,7 @@ SQ_D int decode_name(u32 *nametab, RcDecW &rc, u8 *name_out, u64 room, NameSmem 
         int v = ((int)lj - 32) * 2 + lc2 + k * 64;
         int ctx = v % 8192;
         if (ctx < 0) ctx = 0;
-        u32 ch = wm_decode<128, 4>(middle + (u64)ctx * W128_STRIDE, rc, lane);
+        u32 ch = wm_decode<128, 4>(middle + (u64)ctx * W128_STRIDE, rc, lane, pol);
         if (lane == 0) cur[i] = (u8)ch;
 #define LJ (j < 0 ? 0u : (u32)last[j])
         if (ch == ' ' && LJ != ' ') j++;
@@ -357,12 +381,12 @@ struct SeqPipe {
     SQ_D void init() { step = 0; lc0 = lc1 = lc2 = lc3 = 0xffffffffu; lv0 = lv1 = lv2 = lv3 = 0; }
 };
 
-SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane) {
+SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane, u64 pol) {
     if (lane < SQ_LOOK_N / 4) {
         u32 basec = (last << (2 * SQ_LOOK)) & mask;
         const u8 *src = seqtab + ((u64)basec << 2) + lane * 16;
         u32 dst = (u32)__cvta_generic_to_shared(ring + ((P.step + SQ_LOOK) & 7) * SQ_LOOK_N + lane * 4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(pol) : "memory");
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     u32 *S4 = (u32 *)(seqtab + (u64)last * 4);
@@ -372,7 +396,7 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &la
         __syncwarp();
         x = ring[(P.step & 7) * SQ_LOOK_N + (last & (SQ_LOOK_N - 1))];
     } else {
-        x = *S4;
+        x = ld_hint(S4, pol);
     }
     if (P.lc3 == last) x = P.lv3;
     if (P.lc2 == last) x = P.lv2;
@@ -392,7 +416,7 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &la
     u32 packed = S0 | (S1 << 8) | (S2 << 16) | (S3 << 24);
     u32 inc = 1u << (8 * b);
     u32 nv = (f == 255) ? (packed & ~(0xffu << (8 * b))) : packed + inc;     // (S[b] + 1) & 0xff
-    *S4 = nv;
+    st_hint(S4, nv, pol);
     __syncwarp();
     P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
     P.step++;
@@ -449,6 +473,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
     __shared__ __align__(16) MainSmem sm;
     DecBlock &d = db[blockIdx.x];
     int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 pol = wid == 2 ? l2_policy_stream() : l2_policy_keep();
     if (threadIdx.x == 0) { sm.qprog = 0; sm.side_err = 0; }
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm.rlut[i] = recip_est(i < 2 ? 2 : i);
     __syncthreads();
@@ -477,7 +502,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         u16 *idlen = d.idlen;
         const u64 idcap = d.idcap;
         for (u32 r = 0; r < nreads; r++) {
-            int n = decode_name(nametab, rc, ids + o, idcap - o, sm.ns, lnl, lpl, lsl, lane);
+            int n = decode_name(nametab, rc, ids + o, idcap - o, sm.ns, lnl, lpl, lsl, lane, pol);
             if (n < 0) { if (lane == 0) d.status = SQ_ERR_CAPACITY_K; return; }
             if (lane == 0) idlen[r] = (u16)n;
             o += (u32)n;
@@ -491,14 +516,15 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         u8 *qual = d.qual;
         WReg<3> R;
         u32 last = 0;
-        wm_load(R, tab, lane);                                 // context 0 opens every read
+        wm_load(R, tab, lane, pol);                            // context 0 opens every read
         for (u32 r = 0; r < nreads; r++) {
             u8 *q = qual + seqoff[r];
             int len = seqlen[r];
             u32 delta = 5, q1 = 0, q2 = 0;
             for (int i = 0; i < len; i++) {
                 int kl, li;
-                u32 qq = wm_search<95, 3>(R, rc, lane, kl, li);
+                u32 cex, freq;
+                u32 qq = wm_find<95, 3>(R, rc, lane, kl, li, cex, freq);
                 u32 nlast = 0;
                 bool term = qq == 94;
                 if (!term) {
@@ -511,8 +537,9 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
                 u32 *mp = tab + (u64)last * WQ_STRIDE;
                 WReg<3> Rn;
                 bool same = nlast == last;
-                if (!same) wm_load(Rn, tab + (u64)nlast * WQ_STRIDE, lane);
-                wm_update_store<95, 3>(mp, R, kl, li, lane);
+                if (!same) wm_load(Rn, tab + (u64)nlast * WQ_STRIDE, lane, pol);
+                rc.decode(cex, freq);
+                wm_update_store<95, 3>(mp, R, kl, li, lane, pol);
                 if (!same) R = Rn;
                 last = nlast;
                 if (term) { for (int t = i + lane; t < len; t += 32) q[t] = '#'; break; }
@@ -569,7 +596,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
             bool flagged = r < n_tip && __ldcg(d_tip + r);
             if (!flagged) {
                 for (int i = 0; i < len; i++) {
-                    u32 bb = decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane);
+                    u32 bb = decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol);
                     if (lane == 0) seq[i] = (u8)tbl[bb];
                 }
                 continue;
@@ -585,7 +612,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
                 for (int i = 0; i < len; i++) {
                     u32 c;
                     if (mq >= (int)(int8_t)__ldcg(qual + i)) { c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
-                    else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane)];
+                    else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol)];
                     if (lane == 0) seq[i] = (u8)c;
                 }
                 continue;
@@ -598,10 +625,10 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
                     if (run == gap) {                          // @0x429b40
                         gap = 0xffffffffu;
                         if (remaining) { remaining--; gap = i_pos < n_pos ? __ldcg(d_pos + i_pos) : 0; i_pos++; }
-                        c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane)];
+                        c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol)];
                         run = 0;
                     } else { run++; c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
-                } else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane)];
+                } else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol)];
                 if (lane == 0) seq[i] = (u8)c;
             }
         }

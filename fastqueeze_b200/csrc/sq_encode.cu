@@ -1141,8 +1141,12 @@ cudaError_t sqk_sort(const EncWave &w, int stream, int keybits, u64 *a, u64 *b, 
     u32 maxtiles = cdiv(w.maxbound[stream], SQ_TILE);
     u64 *src = a, *dst = b;
     if (maxtiles == 0) { *sorted = a; return cudaSuccess; }
-    for (int shift = 0; shift < keybits; shift += SQ_SORT_BITS) {
-        CK(sort_pass<SQ_SORT_BITS>(w, stream, src, dst, shift, maxtiles, st, launches));
+    // 17..20 key bits (the default order-10 base context): two passes of 10 bits instead of three of 8
+    const bool wide = keybits > 2 * SQ_SORT_BITS && keybits <= 2 * SQ_SORT_BITS_WIDE;
+    const int step = wide ? SQ_SORT_BITS_WIDE : SQ_SORT_BITS;
+    for (int shift = 0; shift < keybits; shift += step) {
+        if (wide) CK(sort_pass<SQ_SORT_BITS_WIDE>(w, stream, src, dst, shift, maxtiles, st, launches));
+        else CK(sort_pass<SQ_SORT_BITS>(w, stream, src, dst, shift, maxtiles, st, launches));
         u64 *t = src; src = dst; dst = t;
     }
     *sorted = src;
@@ -1158,7 +1162,7 @@ cudaError_t sqk_replay(const EncWave &w, int stream, const u64 *sorted, void *tr
     *launches += 1;
     int nsm = w.nsm;
     if (stream == ST_SEQ) {
-        k_replay_seq<<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, (u32 *)triples_, w.snap_seq, w.train_seq);
+        k_replay_seq<<<nsm * 16, 128, 0, st>>>(sorted, w.bd, w.bs, w.seglist, w.nseg, w.nseg + 1, (u32 *)triples_, w.snap_seq, w.train_seq);
         *launches += 1;
     } else if (stream == ST_QUAL) {
         k_replay_batch<95><<<nsm * 8, 128, 0, st>>>(sorted, w.bd, w.bs, stream, w.seglist, w.nseg, w.nseg + 1, triples,
@@ -1221,5 +1225,9 @@ cudaError_t sqk_enc_attrs() {
                             (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
     CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
+    CK(cudaFuncSetAttribute(k_sort_hist<SQ_SORT_BITS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS_WIDE) * 4));
+    CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS_WIDE) * 4));
     return cudaSuccess;
 }

@@ -10,6 +10,7 @@
 #define SQ_TILE 8192            // sort tile: elements owned by one warp
 #define SQ_SORT_THREADS 256
 #define SQ_SORT_BITS 8          // radix digit width
+#define SQ_SORT_BITS_WIDE 10    // ... for 17..20-bit keys (two passes)
 #define SQ_CHAIN_SMEM_RC (72 * 1024)      // dynamic shared memory requested only to cap chain CTAs per SM
 #define SQ_CHAIN_SMEM_SMALL (36 * 1024)
 
