@@ -11,6 +11,7 @@
 // block): the chains are L2/HBM-latency bound by construction.
 #include "sq_common.cuh"
 #include "sq_kernels.h"
+#include <cstdlib>
 #include "sq_md5.cuh"
 #include <cstdio>
 
@@ -164,12 +165,17 @@ template <int EPL> struct WReg { u32 w[EPL]; u32 bt; };
 // otherwise evict them: models are accessed evict_last, base-context sectors evict_first.
 SQ_D u64 l2_policy_keep() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 SQ_D u64 l2_policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+#ifndef SQ_L2_HINTS
+#define SQ_L2_HINTS 1
+#endif
 SQ_D u32 ld_hint(const u32 *p, u64 pol) {
+    if (SQ_L2_HINTS == 0 || (SQ_L2_HINTS == 2 && pol == 0)) return *(const volatile u32 *)p;
     u32 v;
     asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
     return v;
 }
 SQ_D void st_hint(u32 *p, u32 v, u64 pol) {
+    if (SQ_L2_HINTS == 0 || (SQ_L2_HINTS == 2 && pol == 0)) { *(volatile u32 *)p = v; return; }
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
@@ -455,7 +461,7 @@ struct KModelD {
     }
 };
 struct MainSmem {
-    u32 ring[8 * 256];         // base-model candidate ring of the seq warp (8 slots x up to 256 contexts)
+    u32 ring[8 * SQ_LOOK_N];   // base-model candidate ring of the seq warp (8 slots x 4^SQ_LOOK contexts)
     u32 rlut[1024];            // reciprocal estimates of every possible base-model total (<= 1020)
     NameSmem ns;
     SmModel<2> tip;
@@ -669,6 +675,24 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
         k_init_wm<128, 4><<<dim3(32, B), 256, 0, st>>>(w.db, 1, 8192, 768 * W256_STRIDE,
                                                      w.snap_name ? w.snap_name + 3ull * 256 * 776 : nullptr, 392);
         *launches += 2;
+    }
+    {
+        // The quality / name models are re-read through L1 (measured: bypassing it costs 20 %): ask for
+        // the smallest shared-memory carve-out that still holds this launch's co-resident CTAs.
+        int dev = 0, smem_sm = 228 * 1024;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        int ctas = (B + w.nsm - 1) / (w.nsm > 0 ? w.nsm : 1);
+        int need = ctas * ((int)sizeof(MainSmem) + 1024 + 256);
+        int carve = (int)((100ll * need + smem_sm - 1) / smem_sm);
+        if (carve > 100) carve = 100;
+        const char *e = getenv("SQ_DEC_CARVEOUT");
+        if (e) carve = atoi(e);
+        if (carve >= 0) {
+            cudaFuncSetAttribute(k_dec_main<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(k_dec_main<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(k_dec_main<3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
     }
     k_dec_len<<<B, 32, 0, st>>>(w.db);
     if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
