@@ -24,7 +24,7 @@ EXPORTS = ["sq_create", "sq_destroy", "sq_last_error", "sq_load_model", "sq_mode
 class SqParams(C.Structure):
     _fields_ = [("device", C.c_int32), ("usemodel", C.c_int32), ("lossy", C.c_int32), ("lossy_r", C.c_double),
                 ("md5", C.c_int32), ("slevel", C.c_int32), ("qlevel", C.c_int32), ("id_rule", C.c_int32),
-                ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p)]
+                ("workspace_bytes", C.c_uint64), ("stream", C.c_void_p), ("ref_mode", C.c_int32)]
 
 
 class SqBlockIn(C.Structure):

@@ -44,6 +44,7 @@ class SeqArcParam:
     Qlevel: int = 2
     id_rule: int = 0          # idbin[0]: 1 = rule-based ID path
     modelbuf: bytes = None    # snapshot when usemodel
+    ref_mode: int = 0         # 1 (SE) / 2 (PE): reference index given, nothing mapped (doAlignEncode framing)
 
 
 @dataclass
@@ -71,6 +72,7 @@ class EncapFqzComp:
         p.slevel = self.param.Slevel
         p.qlevel = self.param.Qlevel
         p.id_rule = self.param.id_rule
+        p.ref_mode = self.param.ref_mode
         p.workspace_bytes = workspace_bytes
         p.stream = stream
         self._L = _lib.lib()

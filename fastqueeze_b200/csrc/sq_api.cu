@@ -116,6 +116,7 @@ extern "C" int sq_create(const sq_params *p, sq_ctx **out) {
     if (p->slevel < 0 || p->slevel > 5) { g_create_error = "slevel must be 0..5 (order 7..12)"; return SQ_ERR_ARG; }
     if (p->qlevel < 1 || p->qlevel > 3) { g_create_error = "qlevel must be 1..3"; return SQ_ERR_ARG; }
     if (p->lossy && !(p->lossy_r > 1.0)) { g_create_error = "lossy_r must be > 1"; return SQ_ERR_ARG; }
+    if (p->ref_mode < 0 || p->ref_mode > 2) { g_create_error = "ref_mode must be 0, 1 (SE) or 2 (PE)"; return SQ_ERR_ARG; }
     sq_ctx *c = new sq_ctx();
     c->p = *p;
     auto fail = [&](const std::string &m, int code) { g_create_error = m; sq_destroy(c); return code; };
@@ -254,6 +255,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     EncWave w{};
     w.B = n; w.nsm = c->nsm;
     w.md5 = c->p.md5; w.lossy = c->p.lossy; w.id_rule = c->p.id_rule; w.qlevel = c->p.qlevel;
+    w.ref_mode = c->p.ref_mode;
     w.seqmask = c->nseq() - 1;
     if (train_blob) {            // encodeForModel @0x4228e0: models start from the constructor state
         w.train_name = c->p.id_rule ? nullptr : train_blob;
@@ -673,6 +675,12 @@ int parse_record(const sq_ctx *c, const u8 *rec, u64 reclen, DecBlock &d) {
             pay += 16; sz -= 16;
         }
         if ((tag == 14 || (tag >= 23 && tag <= 26)) && sz < 4) return SQ_ERR_FORMAT;
+        // streams doAlignEncode @0x42d4c0 adds: accepted only when they say "no read of this block mapped"
+        if ((tag >= 17 && tag <= 20) || tag == 22) {
+            if (sz != 4 || pay[0] || pay[1] || pay[2] || pay[3]) return SQ_ERR_FORMAT;
+        } else if ((tag >= 8 && tag <= 13) || tag == 15) {
+            if (sz != 8) return SQ_ERR_FORMAT;
+        }
         d.off[tag] = (u64)(pay - rec);
         d.len[tag] = (u32)sz;
     }

@@ -166,16 +166,18 @@ template <int EPL> struct WReg { u32 w[EPL]; u32 bt; };
 SQ_D u64 l2_policy_keep() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 SQ_D u64 l2_policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 #ifndef SQ_L2_HINTS
-#define SQ_L2_HINTS 1
+#define SQ_L2_HINTS 2          // 0: none, 1: everywhere, 2: base-context accesses only (measured best)
 #endif
+template <bool HINT = (SQ_L2_HINTS == 1)>
 SQ_D u32 ld_hint(const u32 *p, u64 pol) {
-    if (SQ_L2_HINTS == 0 || (SQ_L2_HINTS == 2 && pol == 0)) return *(const volatile u32 *)p;
+    if (!HINT) return *p;
     u32 v;
     asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
     return v;
 }
+template <bool HINT = (SQ_L2_HINTS == 1)>
 SQ_D void st_hint(u32 *p, u32 v, u64 pol) {
-    if (SQ_L2_HINTS == 0 || (SQ_L2_HINTS == 2 && pol == 0)) { *(volatile u32 *)p = v; return; }
+    if (!HINT) { *p = v; return; }
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
@@ -392,7 +394,11 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &la
         u32 basec = (last << (2 * SQ_LOOK)) & mask;
         const u8 *src = seqtab + ((u64)basec << 2) + lane * 16;
         u32 dst = (u32)__cvta_generic_to_shared(ring + ((P.step + SQ_LOOK) & 7) * SQ_LOOK_N + lane * 4);
+#if SQ_L2_HINTS
         asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+#else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+#endif
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     u32 *S4 = (u32 *)(seqtab + (u64)last * 4);
@@ -402,7 +408,7 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &la
         __syncwarp();
         x = ring[(P.step & 7) * SQ_LOOK_N + (last & (SQ_LOOK_N - 1))];
     } else {
-        x = ld_hint(S4, pol);
+        x = ld_hint<(SQ_L2_HINTS != 0)>(S4, pol);
     }
     if (P.lc3 == last) x = P.lv3;
     if (P.lc2 == last) x = P.lv2;
@@ -422,7 +428,7 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &la
     u32 packed = S0 | (S1 << 8) | (S2 << 16) | (S3 << 24);
     u32 inc = 1u << (8 * b);
     u32 nv = (f == 255) ? (packed & ~(0xffu << (8 * b))) : packed + inc;     // (S[b] + 1) & 0xff
-    st_hint(S4, nv, pol);
+    st_hint<(SQ_L2_HINTS != 0)>(S4, nv, pol);
     __syncwarp();
     P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
     P.step++;

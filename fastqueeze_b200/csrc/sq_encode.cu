@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(160) k_side(const BlockDesc *bd, BlockState *b
 // 5. pack: block record "tag 1 | size(4) | count | Len | ID | Qual | Dege* | Seq" (SURVEY App. A;
 // doFqzEncode @0x42d2d0).  k_layout sizes the records (and, for the compact wave buffer, assigns
 // offsets by a scan over blocks); k_pack copies the pieces.
-struct PackCfg { int md5, lossy, id_rule; };
+struct PackCfg { int md5, lossy, id_rule, ref_mode; };
 __constant__ int c_side_tag[6] = {4, 23, 14, 24, 25, 26};
 
 SQ_D u32 id_payload_len(const BlockDesc &d, const BlockState &s, PackCfg cfg) {
@@ -949,8 +949,24 @@ SQ_D u32 id_payload_len(const BlockDesc &d, const BlockState &s, PackCfg cfg) {
     else x += s.olen[ST_NAME];
     return x;
 }
+// Framing doAlignEncode @0x42d4c0 adds when a reference index is loaded but no read mapped (ref_mode
+// 1 = SE, 2 = PE): count records (tag | 0x84 | u32le) and alignment streams with no symbols, i.e. the
+// 8 flush bytes of an untouched range coder.  tested_reads = flags pushed by doAlign @0x411910 /
+// @0x413580 for the head (int)(nreads * 0.05) reads before it gives up (tag 27).
+SQ_D u32 tested_reads(u32 nreads, int pe) {
+    u32 t = (u32)(int)((double)nreads * 0.05);
+    u32 c = pe ? 2 * (t / 2 + 1) : t + 1;
+    return c < nreads ? c : nreads;
+}
+SQ_D u32 put_count(u8 *p, int tag, u32 v) { put_tag(p, tag); p[1] = 0x84; put_u32le(p + 2, v); return 6; }
+SQ_D u32 put_empty_rc(u8 *p, int tag) {
+    put_tag(p, tag); put_size4(p + 1, 8);
+    for (int i = 0; i < 8; i++) p[5 + i] = 0;
+    return 13;
+}
 SQ_D u32 record_len(const BlockDesc &d, const BlockState &s, PackCfg cfg) {
     u32 x = 5 + 6;                                                    // tag 1 + size4, count record
+    if (cfg.ref_mode) x += 6 + 13 + 4 * 6 + (cfg.ref_mode == 2 ? 6 + 6 + 13 : 0) + 5 * 13;
     x += 5 + s.side_len[0];                                           // Len
     x += 5 + id_payload_len(d, s, cfg);
     x += 5 + ((cfg.md5 && !cfg.lossy) ? 16 : 0) + s.olen[ST_QUAL];
@@ -1023,6 +1039,10 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDesc *bd, const BlockSt
     p += 5;
     copy_bytes(rec + p, sidebuf + d.sidebase, s.side_len[0], tid, nthr);   // Len region is at offset 0
     p += s.side_len[0];
+    if (cfg.ref_mode) {                                           // @0x42d547-0x42d56f: tag 27, compressOrder (tag 8)
+        if (w0) { put_count(rec + p, 27, tested_reads(d.nreads, cfg.ref_mode == 2)); put_empty_rc(rec + p + 6, 8); }
+        p += 6 + 13;
+    }
     // ID (tag 5)
     u32 idl = id_payload_len(d, s, cfg);
     if (w0) { put_tag(rec + p, 5); put_size4(rec + p + 1, idl); }
@@ -1044,6 +1064,16 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDesc *bd, const BlockSt
     if (qmd5) { copy_bytes(rec + p, s.md5[2], 16, tid, nthr); p += 16; }
     copy_bytes(rec + p, obuf + d.obase[ST_QUAL], s.olen[ST_QUAL], tid, nthr);
     p += s.olen[ST_QUAL];
+    if (cfg.ref_mode) {                                           // @0x42d5bd-0x42d6c7 (PE part @0x42d830)
+        if (w0) {
+            u8 *q = rec + p;
+            for (int t = 17; t <= 20; t++) q += put_count(q, t, 0);
+            if (cfg.ref_mode == 2) { q += put_count(q, 21, 9); q += put_count(q, 22, 0); q += put_empty_rc(q, 9); }
+            const int tags[5] = {11, 15, 10, 12, 13};             // Pos, Mis, Rev, CigaL, CigaV
+            for (int k = 0; k < 5; k++) q += put_empty_rc(q, tags[k]);
+        }
+        p += 4 * 6 + (cfg.ref_mode == 2 ? 6 + 6 + 13 : 0) + 5 * 13;
+    }
     // Dege streams (tags 23, 14, 24, 25, 26): u32le count + range-coder bytes, omitted when empty
     {
         u64 o = 6ull * d.nreads + 16;                              // region offsets as laid out by k_side
@@ -1206,7 +1236,7 @@ cudaError_t sqk_side(const EncWave &w, cudaStream_t st, u64 *launches) {
 }
 
 cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launches) {
-    PackCfg cfg{w.md5, w.lossy, w.id_rule};
+    PackCfg cfg{w.md5, w.lossy, w.id_rule, w.ref_mode};
     k_layout<<<1, 1024, 0, st>>>(w.bd, w.bs, w.B, cfg, w.recbuf, w.recbuf_cap, w.recoff, compact);
     k_pack<<<dim3(32, w.B), 256, 0, st>>>(w.bd, w.bs, cfg, w.obuf, w.sidebuf);
     *launches += 2;

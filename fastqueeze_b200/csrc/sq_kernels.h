@@ -20,6 +20,7 @@ struct EncWave {
     u32 R;                      // reads in the wave
     int nsm;                    // SM count (persistent-kernel grid sizing)
     int md5, lossy, id_rule, qlevel;
+    int ref_mode;               // 0, or 1 (SE) / 2 (PE): frame the empty alignment streams of doAlignEncode
     u32 seqmask;                // 4^NS - 1
     BlockDesc *bd;
     BlockState *bs;

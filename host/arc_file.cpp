@@ -46,7 +46,8 @@ bool ArcWriter::finish(const ArcParams &p) {
     auto b1 = [&](int id, bool v) { uint8_t x = v; put_param(par, id, &x, 1); };
     auto u16 = [&](int id, uint16_t v) { uint8_t x[2] = {(uint8_t)v, (uint8_t)(v >> 8)}; put_param(par, id, x, 2); };
     auto u32 = [&](int id, uint32_t v) { uint8_t x[4] = {(uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24)}; put_param(par, id, x, 4); };
-    b1(1, true); b1(2, true);            // constant in every no-reference archive the reference writes
+    b1(1, !p.has_ref);                   // 1 = no reference index
+    b1(2, true);
     b1(3, !p.pe);                        // single-end
     b1(4, false); b1(5, true);
     b1(6, p.usemodel);
@@ -68,6 +69,10 @@ bool ArcWriter::finish(const ArcParams &p) {
         const uint8_t h[4] = {0x81, 0x82, 0x01, 0x00};
         tr.insert(tr.end(), h, h + 4);
         tr.insert(tr.end(), p.model.begin(), p.model.end());
+    }
+    if (p.has_ref) {
+        put_id(tr, 8); put_vint(tr, 16, 1);
+        tr.insert(tr.end(), p.ref_md5, p.ref_md5 + 16);
     }
     std::vector<uint8_t> ix;
     for (auto &b : idx_) {
@@ -140,7 +145,8 @@ bool ArcReader::load(const std::string &path) {
                 uint64_t id, ps;
                 k = get_vint(a, ae, &id); if (!k) break; a += k;
                 k = get_vint(a, ae, &ps); if (!k || a + k + ps > ae) break; a += k;
-                if (id == 3 && ps == 1) p.pe = !a[0];
+                if (id == 1 && ps == 1) p.has_ref = !a[0];
+                else if (id == 3 && ps == 1) p.pe = !a[0];
                 else if (id == 6 && ps == 1) p.usemodel = a[0];
                 else if (id == 13) p.name1.assign((const char *)a, ps);
                 else if (id == 14) p.name2.assign((const char *)a, ps);
@@ -152,6 +158,8 @@ bool ArcReader::load(const std::string &path) {
         } else if (tag == 6) {
             if (sz < 4) { err = "bad model entry"; return false; }
             p.model.assign(pay + 4, pay + sz);
+        } else if (tag == 8 && sz == 16) {
+            memcpy(p.ref_md5, pay, 16);
         } else if (tag == 7) {
             ix.assign(pay, pay + sz);
         }

@@ -19,6 +19,8 @@ struct ArcParams {
     std::string name1, name2;      // params 13 / 14: base names of the inputs
     uint8_t idbin[512] = {0};      // param 15: ID-bin types (idbin[0] = 1: rule-based ID path)
     std::vector<uint8_t> model;    // trailer TAG 6 payload after its "TAG 1, u16 = 1" header
+    bool has_ref = false;          // param 1 is 0 and trailer TAG 8 holds the MD5 of the reference FASTA
+    uint8_t ref_md5[16] = {0};     // (SeqArcFile::writeMd5 @0x416ba0, after the model, before the block index)
 };
 
 struct BlockIndex {                // one record of trailer TAG 7 (32 B single-end, 40 B paired-end)

@@ -33,7 +33,7 @@ int sqh_cut_blocks(const char *p1, const char *p2, uint64_t block_bytes, uint32_
 // Write an archive from ready-made block records (concatenated in `recs`, lengths in `lens`).
 int sqh_write_arc(const char *path, int pe, int usemodel, int lossy, int md5, const char *name1, const char *name2,
                   const uint8_t *idbin, const uint8_t *model, uint64_t modellen, const uint8_t *recs, const uint64_t *lens,
-                  const uint64_t *src1, const uint64_t *src2, int nblocks) {
+                  const uint64_t *src1, const uint64_t *src2, int nblocks, const uint8_t *ref_md5) {
     ArcWriter w;
     if (!w.open(path)) return -1;
     uint64_t o = 0, so[2] = {0, 0};
@@ -48,6 +48,7 @@ int sqh_write_arc(const char *path, int pe, int usemodel, int lossy, int md5, co
     p.name1 = name1 ? name1 : ""; p.name2 = name2 ? name2 : "";
     if (idbin) memcpy(p.idbin, idbin, 512);
     if (model) p.model.assign(model, model + modellen);
+    if (ref_md5) { p.has_ref = true; memcpy(p.ref_md5, ref_md5, 16); }     // archive written against a reference index
     return w.finish(p) ? 0 : -1;
 }
 

@@ -26,6 +26,7 @@ struct Opt {
     bool compress = false, decompress = false, force = false, md5 = true, lossy = false;
     double lossy_r = 0;
     std::string in1, in2, out, arc;
+    std::string ref;            // reference FASTA given on the command line (SeqArc -c [ref.fa] ... / -d [ref.fa] x.arc)
     int block_mb = 50, slevel = 3, qlevel = 2, device = 0, batch = 0;
     bool verbose = false;
 };
@@ -58,8 +59,9 @@ static bool exists(const std::string &p) { struct stat st; return stat(p.c_str()
 
 static void die(const std::string &m) { fprintf(stderr, "seqarc_b200: %s\n", m.c_str()); exit(1); }
 
-static sq_ctx *make_ctx(const Opt &o, bool usemodel, bool lossy, double r, bool md5, int id_rule) {
+static sq_ctx *make_ctx(const Opt &o, bool usemodel, bool lossy, double r, bool md5, int id_rule, int ref_mode = 0) {
     sq_params p{};
+    p.ref_mode = ref_mode;
     p.device = o.device; p.usemodel = usemodel; p.lossy = lossy; p.lossy_r = r; p.md5 = md5;
     p.slevel = o.slevel; p.qlevel = o.qlevel; p.id_rule = id_rule;
     sq_ctx *c = nullptr;
@@ -123,6 +125,28 @@ static int do_compress(const Opt &o) {
     ArcParams ap;
     ap.pe = pe; ap.usemodel = usemodel; ap.lossy = o.lossy; ap.md5 = o.md5;
     ap.name1 = base_name(o.in1); ap.name2 = base_name(o.in2);
+    if (!o.ref.empty()) {
+        // A reference index turns on doAlignEncode @0x42d4c0.  Alignment itself is outside this path: every read is
+        // coded as unmapped, which is what the reference writes when nothing maps ("Align block:0") -- same entropy
+        // streams, empty alignment streams, param 1 = 0 and the reference's MD5 (the <ref>.md5 file `SeqArc -i`
+        // leaves beside the index, i.e. the MD5 of the FASTA file) in trailer TAG 8.
+        ap.has_ref = true;
+        std::vector<uint8_t> d;
+        FILE *f = fopen((o.ref + ".md5").c_str(), "rb");
+        if (f) { d.resize(16); if (fread(d.data(), 1, 16, f) != 16) d.clear(); fclose(f); }
+        if (d.size() == 16) memcpy(ap.ref_md5, d.data(), 16);
+        else {
+            f = fopen(o.ref.c_str(), "rb");
+            if (!f) die("cannot open reference " + o.ref);
+            std::vector<uint8_t> all;
+            uint8_t buf[1 << 16];
+            size_t n;
+            while ((n = fread(buf, 1, sizeof buf, f)) > 0) all.insert(all.end(), buf, buf + n);
+            fclose(f);
+            md5_digest(all.data(), all.size(), ap.ref_md5);
+        }
+        if (o.verbose) fprintf(stderr, "reference given: reads are not aligned, every block is written as an all-unmapped block\n");
+    }
     // SeqArcPreProcess::doPreProcess @0x4153b0: the ID-bin analysis runs over the head sample blocks and stops
     // at the first block whose IDs are not rule-predictable; the same blocks train the snapshot when usemodel
     std::vector<MemBuf> sample;
@@ -131,7 +155,7 @@ static int do_compress(const Opt &o) {
     for (auto &m : sample)
         if (okbins) okbins = analyse_id_bins(m, pe, ap.idbin);
     if (o.verbose) fprintf(stderr, "bOrderBin %d petype %d\n", ap.idbin[0], ap.idbin[1]);
-    sq_ctx *c = make_ctx(o, usemodel, o.lossy, o.lossy_r, o.md5, ap.idbin[0]);
+    sq_ctx *c = make_ctx(o, usemodel, o.lossy, o.lossy_r, o.md5, ap.idbin[0], ap.has_ref ? (pe ? 2 : 1) : 0);
     if (usemodel) {
         std::vector<sq_block_in> in;
         for (auto &m : sample) in.push_back(as_in(m));
@@ -292,10 +316,11 @@ int main(int argc, char **argv) {
         else if (a == "-l") { o.lossy = true; o.lossy_r = atof(val().c_str()); }
         else if (a == "-g") o.device = atoi(val().c_str());
         else if (a == "-b") o.batch = atoi(val().c_str());
-        else if (a == "-h") { printf("usage: seqarc_b200 -c -1 a.fq [-2 b.fq] -o out [-l r] [-n] [-f] | -d in.arc -o out [-f]\n"); return 0; }
-        else if (a[0] != '-') o.arc = a;
+        else if (a == "-h") { printf("usage: seqarc_b200 -c [ref.fa] -1 a.fq [-2 b.fq] -o out [-l r] [-n] [-f] | -d [ref.fa] in.arc -o out [-f]\n"); return 0; }
+        else if (a[0] != '-') { if (!o.arc.empty()) o.ref = o.arc; o.arc = a; }   // [ref.fa] precedes the archive
         else die("unknown option " + a);
     }
+    if (o.compress && o.ref.empty()) { o.ref = o.arc; o.arc.clear(); }            // -c [ref.fa] -1 ... -o ...
     try {
         if (o.compress && !o.in1.empty() && !o.out.empty()) return do_compress(o);
         if (o.decompress && !o.arc.empty() && !o.out.empty()) return do_decompress(o);

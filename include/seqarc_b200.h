@@ -51,6 +51,11 @@ typedef struct {
     int32_t id_rule;       /* SeqArcParam+0x18a4 idbin[0]: 1 = rule-based ID path (first ID only) */
     uint64_t workspace_bytes;  /* device workspace budget; 0 = 80 % of free device memory */
     void   *stream;        /* cudaStream_t to launch on, or NULL for a private stream */
+    int32_t ref_mode;      /* 0: no reference index.  1 (SE) / 2 (PE): the archive is written against a reference
+                              index and no read of the block mapped (BASELINE configs[4]): doAlignEncode @0x42d4c0
+                              frames the same ID / quality / base streams plus empty alignment streams (tags 27, 8,
+                              17-22, 9, 11, 15, 10, 12, 13).  Blocks holding mapped reads are out of scope: the
+                              decoder answers SQ_ERR_FORMAT for them */
 } sq_params;
 
 /* One block as SeqArcMemBuf holds it at the doFqzEncode seam: concatenated buffers

@@ -20,7 +20,7 @@ class Params(C.Structure):
     _fields_ = [("usemodel", C.c_int32), ("lossy", C.c_int32), ("lossy_r", C.c_double),
                 ("md5", C.c_int32), ("slevel", C.c_int32), ("qlevel", C.c_int32),
                 ("id_rule", C.c_int32), ("idbin", C.c_void_p), ("model", C.c_void_p),
-                ("modellen", C.c_uint64)]
+                ("modellen", C.c_uint64), ("ref_mode", C.c_int32)]
 
 
 class CBlock(C.Structure):
@@ -97,8 +97,9 @@ def lib():
 
 class Oracle:
     def __init__(self, usemodel=0, lossy=0, lossy_r=0.0, md5=1, slevel=3, qlevel=2, id_rule=0,
-                 idbin=None, model=None):
+                 idbin=None, model=None, ref_mode=0):
         self.p = Params()
+        self.p.ref_mode = ref_mode
         self.p.usemodel, self.p.lossy, self.p.lossy_r = usemodel, lossy, lossy_r
         self.p.md5, self.p.slevel, self.p.qlevel, self.p.id_rule = md5, slevel, qlevel, id_rule
         self._idbin = np.frombuffer(idbin, dtype=np.uint8).copy() if idbin is not None else None

@@ -563,6 +563,29 @@ void sqo_md5(const uint8_t *data, uint64_t n, uint8_t digest[16]) {
     for (int k = 0; k < 4; k++) put_u32le(digest + 4 * k, h[k]);
 }
 
+/* Framing added by doAlignEncode @0x42d4c0 when a reference index is loaded but nothing mapped.
+ * compressCount(tag, v) @0x422a00 = tag | 0x84 | u32le; an alignment stream with no symbols is the
+ * 8 flush bytes of an untouched range coder.  tested_reads: AlignEncodeSEJob::doAlign @0x411910 /
+ * AlignEncodePEJob::doAlign @0x413580 try the head of the block -- (int)(nreads * 0.05) reads, constant
+ * @0x44a218 -- pushing one flag per tried read into membuf+0xe0 (count at +0xe8, written as tag 27),
+ * and give up at the first ratio check when none mapped. */
+static int put_count(uint8_t *p, int tag, uint32_t v) {
+    int n = put_id(p, (uint64_t)tag);
+    p[n] = 0x84; put_u32le(p + n + 1, v);
+    return n + 5;
+}
+static int put_empty_rc(uint8_t *p, int tag) {
+    int n = put_id(p, (uint64_t)tag);
+    put_size(p + n, 8, 4);
+    memset(p + n + 4, 0, 8);
+    return n + 12;
+}
+uint32_t sqo_tested_reads(uint32_t nreads, int pe) {
+    uint32_t t = (uint32_t)(int)((double)nreads * 0.05);
+    uint32_t c = pe ? 2 * (t / 2 + 1) : t + 1;
+    return c < nreads ? c : nreads;
+}
+
 /* ------------------------------------------------------------------ doFqzEncode @0x42d2d0 */
 int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t cap) {
     (void)cap;
@@ -579,6 +602,10 @@ int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t 
     p += put_id(p, 1); *p++ = 0x84; put_u32le(p, b->nreads); p += 4;
     /* Len: tag 4 */
     { p += put_id(p, 4); uint8_t *s = p; p += 4; int64_t n = sqo_stream_len(c, b, p); put_size(s, n, 4); p += n; }
+    if (c->p.ref_mode) {                                              /* @0x42d547-0x42d56f */
+        p += put_count(p, 27, sqo_tested_reads(b->nreads, c->p.ref_mode == 2));
+        p += put_empty_rc(p, 8);                                      /* compressOrder @0x424b70 */
+    }
     /* ID: tag 5 (compressID @0x4247c0) */
     {
         p += put_id(p, 5); uint8_t *s = p; p += 4; uint8_t *st = p;
@@ -595,6 +622,16 @@ int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t 
         if (c->p.md5 && !c->p.lossy) { memcpy(p, md5[2], 16); p += 16; }
         p += sqo_stream_qual(c, b, p);
         put_size(s, p - st, 4);
+    }
+    if (c->p.ref_mode) {                                              /* @0x42d5bd-0x42d6c7, PE part @0x42d830 */
+        for (int t = 17; t <= 20; t++) p += put_count(p, t, 0);
+        if (c->p.ref_mode == 2) {
+            p += put_count(p, 21, 9);                                 /* membuf+0x28: 9 on every PE archive observed */
+            p += put_count(p, 22, 0);
+            p += put_empty_rc(p, 9);                                  /* compressPERelation @0x422be0 */
+        }
+        static const int tags[5] = {11, 15, 10, 12, 13};              /* Pos, Mis, Rev, CigaL, CigaV */
+        for (int k = 0; k < 5; k++) p += put_empty_rc(p, tags[k]);
     }
     kmodel_init(c);                                                   /* @0x42d391 */
     p += emit_small_sm(p, 23, 2, d.tip, d.n_tip, 0);

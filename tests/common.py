@@ -95,6 +95,9 @@ def case_params(name):
               slevel=int(cfg.get("Slevel", 3)), qlevel=int(cfg.get("Qlevel", 2)), id_rule=int(idbin[0]))
     if kw["usemodel"]:
         kw["model"] = arc["trailer"]["model"][4:]
+    if m.get("ref"):        # reference index given, nothing mapped: doAlignEncode framing
+        kw["ref_mode"] = 2 if m["pe"] else 1
+        assert arc["trailer"][8].hex() == m["ref_md5"] and arc["trailer"]["params"][1] == b"\x00"
     if "-l" in m["opts"]:
         kw["lossy"] = 1
         kw["lossy_r"] = float(m["opts"][m["opts"].index("-l") + 1])
@@ -133,7 +136,7 @@ def to_param(kw, model=None):
     from fastqueeze_b200 import SeqArcParam
     return SeqArcParam(usemodel=kw["usemodel"], lossy=kw["lossy"], lossy_r=kw["lossy_r"], md5=kw["md5"],
                        Slevel=kw["slevel"], Qlevel=kw["qlevel"], id_rule=kw["id_rule"],
-                       modelbuf=model if model is not None else kw.get("model"))
+                       modelbuf=model if model is not None else kw.get("model"), ref_mode=kw.get("ref_mode", 0))
 
 
 def synth_block(**kw):

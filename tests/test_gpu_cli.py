@@ -17,7 +17,9 @@ CLI = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
 
 # every golden archive, rule-predictable IDs (ERR / SRR style) included: byte identity expected
 IDENTICAL = ["err_pe1000", "err_pe1000_nomd5", "srr_pe100", "illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
-             "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel", "illumina_pe150_usemodel"]
+             "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel", "illumina_pe150_usemodel",
+             # BASELINE configs[4]: reference index given, nothing maps
+             "illumina_pe150_ref", "se100_q8_ref", "err_pe1000_ref", "illumina_pe150_ref_3blocks"]
 
 
 def _setup(name, d):
@@ -29,6 +31,14 @@ def _setup(name, d):
         p = os.path.join(d, "in_%d.fq" % (k + 1))
         open(p, "wb").write(t)
         paths.append(p)
+    if m.get("ref"):
+        # the CLI takes the reference's MD5 from the <ref>.md5 file `SeqArc -i` leaves beside the index, or else
+        # digests the FASTA itself: the SE case exercises the second path
+        if m["pe"]:
+            open(os.path.join(d, "ref.fa.md5"), "wb").write(bytes.fromhex(m["ref_md5"]))
+        else:
+            from tools.make_golden import random_reference
+            open(os.path.join(d, "ref.fa"), "wb").write(random_reference(**m["ref"]))
     cfg = m["config"] or {}
     if cfg:
         with open(os.path.join(d, "seqarc.config"), "w") as f:
@@ -38,7 +48,7 @@ def _setup(name, d):
 
 
 def _compress(m, paths, d, out="out"):
-    args = [CLI, "-c", "-f", "-1", paths[0]] + (["-2", paths[1]] if m["pe"] else []) + ["-o", out] + m["opts"]
+    args = [CLI, "-c", "-f"] + (["ref.fa"] if m.get("ref") else []) + ["-1", paths[0]] + (["-2", paths[1]] if m["pe"] else []) + ["-o", out] + m["opts"]
     env = dict(os.environ)
     if m.get("usemodel"):
         env["SQ_FORCE_USEMODEL"] = "1"       # the golden was made with the size-faking shim

@@ -45,6 +45,14 @@ CASES = [
          config={"BlockSize(M)": 1}, fake_size=15000000000),
     dict(name="illumina_pe150_usemodel", src=dict(kind="illumina_pe150", n_templates=3200, seed=41), pe=True, opts=[],
          config={"BlockSize(M)": 1}, fake_size=8000000000),
+    # BASELINE configs[4]: a random reference index is given and nothing maps ("Align block:0"): doAlignEncode framing
+    dict(name="illumina_pe150_ref", src=dict(kind="illumina_pe150", n_templates=1500, seed=7), pe=True, opts=[], config=None,
+         ref=dict(n=2000000, seed=5)),
+    dict(name="se100_q8_ref", src=dict(kind="se100_q8", n_templates=4000, seed=12345), pe=False, opts=[], config=None,
+         ref=dict(n=2000000, seed=5)),
+    dict(name="err_pe1000_ref", src="err", pe=True, opts=[], config=None, ref=dict(n=2000000, seed=5)),
+    dict(name="illumina_pe150_ref_3blocks", src=dict(kind="illumina_pe150", n_templates=3200, seed=31), pe=True, opts=[],
+         config={"BlockSize(M)": 1}, ref=dict(n=2000000, seed=5)),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
@@ -59,7 +67,16 @@ def case_fastq(case):
     return t if case["pe"] else (t,)
 
 
+def random_reference(n, seed):
+    """FASTA text of one random chromosome (numpy default_rng(seed), 60 bases per line)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
+    return b">chr1\n" + b"".join(s[i:i + 60].tobytes() + b"\n" for i in range(0, n, 60))
+
+
 def main():
+    only = set(sys.argv[1:])        # optional: regenerate only the named cases, keep the other manifest entries
     os.makedirs(GOLD, exist_ok=True)
     assert po.have_ref(), "reference binary not staged (make -C oracle ref)"
     # committed real-data subset: first 1000 pairs of the reference's own test files
@@ -71,8 +88,10 @@ def main():
             with open(dst, "wb") as f:
                 with gzip.GzipFile(fileobj=f, mode="wb", mtime=0) as g:
                     g.write(b"\n".join(lines) + b"\n")
-    manifest = {}
+    manifest = json.load(open(os.path.join(GOLD, "manifest.json"))) if only else {}
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         fq = case_fastq(case)
         tmp = tempfile.mkdtemp(prefix="gold_")
         try:
@@ -82,6 +101,15 @@ def main():
                 open(p, "wb").write(t)
                 names.append(p)
             args = ["-c", "-t", "1", "-f"] + case["opts"]
+            ref_md5 = None
+            if case.get("ref"):     # `SeqArc -i` writes a ~2 GB hash index beside the FASTA (temporary)
+                fa = random_reference(**case["ref"])
+                open(os.path.join(tmp, "ref.fa"), "wb").write(fa)
+                rc, log = po.run_ref(["-i", "ref.fa"], tmp)
+                assert rc == 0, log[-2000:]
+                ref_md5 = open(os.path.join(tmp, "ref.fa.md5"), "rb").read().hex()
+                assert ref_md5 == hashlib.md5(fa).hexdigest()
+                args += ["ref.fa"]
             if case["pe"]:
                 args += ["-1", names[0], "-2", names[1]]
             else:
@@ -90,10 +118,14 @@ def main():
             rc, log = po.run_ref(args, tmp, lossy_shim=case.get("shim", False), config=case["config"],
                                  fake_size=case.get("fake_size"))
             assert rc == 0, (case["name"], rc, log[-2000:])
+            if case.get("ref"):
+                assert "Align block:0" in log, log[-1500:]
             arc = open(os.path.join(tmp, "out.arc"), "rb").read()
             entry = dict(src=case["src"], pe=case["pe"], opts=case["opts"], config=case["config"],
                          shim=case.get("shim", False), arc_bytes=len(arc), arc_md5=hashlib.md5(arc).hexdigest(),
                          fastq_md5=[hashlib.md5(t).hexdigest() for t in fq])
+            if ref_md5:
+                entry.update(ref=case["ref"], ref_md5=ref_md5)
             if case.get("fake_size"):
                 from oracle import arcwalk
                 assert "usemodel=1" in log, log[-1500:]
