@@ -488,6 +488,12 @@ def main():
         if top == "dec.decode" and usemodel:
             alg_bytes += nblocks * 27_203_584          # the snapshot is read once per block to restore the models
         achieved = alg_bytes / 1e9 / (mean_ms[top] / 1e3)
+        # DRAM bytes of that kernel per launch, from the ncu capture of this command on the full job
+        # (profiles/r1f_traffic_k_dec_main.csv: dram__bytes_read.sum + dram__bytes_write.sum); only quoted for
+        # the configuration it was measured on
+        traffic = None
+        if top == "dec.decode" and nblocks == 274 and usemodel:
+            traffic = 1_074_329_448_960 + 549_005_104_896
         out = {
             "metric": "FASTQ MB/s compress+decompress (entropy stage)", "value": round(value, 2), "unit": "MB/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 2),
@@ -502,7 +508,8 @@ def main():
             "gpu_launches": int(n_launch),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": None,
+                         "frac": round(achieved / peak, 5), "traffic": traffic,
+                         "traffic_source": "profiles/r1f_traffic_k_dec_main.csv (ncu, k_dec_main, one launch)" if traffic else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": int(alg_bytes)},
             "e2e": e2e, "cpu_baseline": cpu,
