@@ -47,9 +47,9 @@ bool ArcWriter::finish(const ArcParams &p) {
     auto u16 = [&](int id, uint16_t v) { uint8_t x[2] = {(uint8_t)v, (uint8_t)(v >> 8)}; put_param(par, id, x, 2); };
     auto u32 = [&](int id, uint32_t v) { uint8_t x[4] = {(uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24)}; put_param(par, id, x, 4); };
     b1(1, !p.has_ref);                   // 1 = no reference index
-    b1(2, true);
+    b1(2, !p.comment);                   // 1 = bare '+' lines
     b1(3, !p.pe);                        // single-end
-    b1(4, false); b1(5, true);
+    b1(4, p.gz); b1(5, true);
     b1(6, p.usemodel);
     b1(7, false);
     u16(8, 1); u16(9, 6);                // format version 1.6
@@ -78,7 +78,7 @@ bool ArcWriter::finish(const ArcParams &p) {
     for (auto &b : idx_) {
         le(ix, (uint64_t)b.len * 2, 4);                  // low bit: long-read flag
         if (p.pe) { le(ix, b.src_bytes[0], 4); le(ix, b.src_bytes[1], 4); }
-        else { le(ix, 1, 4); le(ix, b.src_bytes[0], 4); }
+        else { le(ix, p.comment ? 0 : 1, 4); le(ix, b.src_bytes[0], 4); }
         le(ix, 0, 4);
         le(ix, b.arc_off, 8);
         le(ix, b.src_off[0], 8);
@@ -146,7 +146,9 @@ bool ArcReader::load(const std::string &path) {
                 k = get_vint(a, ae, &id); if (!k) break; a += k;
                 k = get_vint(a, ae, &ps); if (!k || a + k + ps > ae) break; a += k;
                 if (id == 1 && ps == 1) p.has_ref = !a[0];
+                else if (id == 2 && ps == 1) p.comment = !a[0];
                 else if (id == 3 && ps == 1) p.pe = !a[0];
+                else if (id == 4 && ps == 1) p.gz = a[0];
                 else if (id == 6 && ps == 1) p.usemodel = a[0];
                 else if (id == 13) p.name1.assign((const char *)a, ps);
                 else if (id == 14) p.name2.assign((const char *)a, ps);

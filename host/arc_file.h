@@ -16,6 +16,8 @@ struct ArcParams {
     bool usemodel = false;         // param 6
     bool lossy = false;            // param 16
     bool md5 = true;               // param 17
+    bool gz = false;               // param 4: the input was gzip-compressed
+    bool comment = false;          // param 2 is 0 when the '+' lines repeat the ID (SE index records then carry 0, not 1)
     std::string name1, name2;      // params 13 / 14: base names of the inputs
     uint8_t idbin[512] = {0};      // param 15: ID-bin types (idbin[0] = 1: rule-based ID path)
     std::vector<uint8_t> model;    // trailer TAG 6 payload after its "TAG 1, u16 = 1" header

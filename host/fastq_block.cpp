@@ -1,18 +1,53 @@
 #include "fastq_block.h"
 
+#include <zlib.h>
+
+#include <algorithm>
+
 #include <cstring>
 #include <stdexcept>
 
 namespace sqhost {
 
+bool InFile::open(const std::string &path) {
+    close();
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (g) gzbuffer(g, 1 << 20);
+    f_ = g;
+    return f_ != nullptr;
+}
+void InFile::close() {
+    if (f_) gzclose((gzFile)f_);
+    f_ = nullptr;
+}
+size_t InFile::read(void *dst, size_t n) {
+    size_t got = 0;
+    while (got < n) {
+        unsigned chunk = (unsigned)std::min<size_t>(n - got, 1u << 30);
+        int r = gzread((gzFile)f_, (char *)dst + got, chunk);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    return got;
+}
+bool InFile::getline(std::vector<char> &out) {
+    char buf[1 << 16];
+    bool any = false;
+    while (gzgets((gzFile)f_, buf, sizeof buf)) {
+        size_t n = strlen(buf);
+        out.insert(out.end(), buf, buf + n);
+        any = true;
+        if (n && buf[n - 1] == '\n') break;
+    }
+    return any;
+}
+
 BlockReader::BlockReader(const std::string &p1, const std::string &p2, uint64_t block_bytes) : block_bytes_(block_bytes) {
     pe_ = !p2.empty();
-    f_[0] = fopen(p1.c_str(), "rb");
-    if (pe_) f_[1] = fopen(p2.c_str(), "rb");
+    f_[0].open(p1);
+    if (pe_) f_[1].open(p2);
 }
-BlockReader::~BlockReader() {
-    for (auto f : f_) if (f) fclose(f);
-}
+BlockReader::~BlockReader() {}
 
 // getEndPos @0x4320c0: scan backwards from index `len` for buf[p] == '\n' && buf[p+1] == '@' such that
 // buf[p+1+k] == firstline[k] holds for 6 CONSECUTIVE k somewhere in [0, |firstline|).  Bytes at or
@@ -50,7 +85,7 @@ bool BlockReader::next_text(std::vector<char> &t1, std::vector<char> &t2) {
         memcpy(b.data(), left_[k].data(), L);
         left_[k].clear();
         size_t want = quota > L ? quota - L : 0;
-        size_t got = want ? fread(b.data() + L, 1, want, f_[k]) : 0;
+        size_t got = want ? f_[k].read(b.data() + L, want) : 0;
         if (first_[k].empty()) first_line(b.data() + L, got, first_[k]);
         if (got < want) shortread = true;
         b.resize(L + got);
@@ -115,12 +150,15 @@ void parse_block(const std::vector<char> &t1, const std::vector<char> &t2, bool 
     mb.ids.reserve(t1.size() / 4 + t2.size() / 4);
     mb.seq.reserve((t1.size() + t2.size()) / 2);
     mb.qual.reserve((t1.size() + t2.size()) / 2);
+    mb.comment = nrec && ll[0][2] > 1;
     for (size_t r = 0; r < nrec; r++) {
         for (int k = 0; k < (pe ? 2 : 1); k++) {
             const char *id = ln[k][4 * r], *sq = ln[k][4 * r + 1], *pl = ln[k][4 * r + 2], *ql = ln[k][4 * r + 3];
             int il = ll[k][4 * r], sl = ll[k][4 * r + 1], pll = ll[k][4 * r + 2], qll = ll[k][4 * r + 3];
             if (il < 1 || id[0] != '@' || pll < 1 || pl[0] != '+') throw std::runtime_error("malformed FASTQ record");
-            if (pll != 1) throw std::runtime_error("'+' lines that repeat the ID are not supported");
+            // the archive only records WHETHER the '+' lines repeat the ID (the reference's own round trip fails on a mix)
+            if (mb.comment ? (pll != il || memcmp(pl + 1, id + 1, (size_t)il - 1) != 0) : pll != 1)
+                throw std::runtime_error("'+' lines must be all bare or all a copy of the ID");
             if (sl != qll) throw std::runtime_error("sequence and quality lengths differ");
             if (il - 1 > 255) throw std::runtime_error("read ID longer than 255 bytes (limit of the reference's name model)");
             mb.ids.insert(mb.ids.end(), id + 1, id + il);
@@ -151,7 +189,9 @@ void render_block(const MemBuf &mb, bool pe, std::string &o1, std::string &o2) {
         o.append((const char *)mb.ids.data() + io, mb.idlen[r]);
         o.push_back('\n');
         o.append((const char *)mb.seq.data() + so, mb.seqlen[r]);
-        o.append("\n+\n");
+        o.append("\n+");
+        if (mb.comment) o.append((const char *)mb.ids.data() + io, mb.idlen[r]);
+        o.push_back('\n');
         o.append((const char *)mb.qual.data() + so, mb.seqlen[r]);
         o.push_back('\n');
         io += mb.idlen[r];

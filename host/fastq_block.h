@@ -25,7 +25,26 @@ struct MemBuf {
     std::vector<int32_t> seqlen;
     uint64_t src_bytes[2] = {0, 0};     // FASTQ bytes this block took from file 1 / file 2
     uint64_t src_off[2] = {0, 0};       // their offsets in the source files
+    bool comment = false;               // the '+' lines repeat the ID (trailer param 2 = 0); decided by the block's first record
     uint32_t nreads() const { return (uint32_t)seqlen.size(); }
+};
+
+// FASTQ input, plain or gzip (the reference reads both; zlib's gz layer passes plain files through).
+class InFile {
+public:
+    InFile() = default;
+    InFile(const InFile &) = delete;
+    InFile &operator=(const InFile &) = delete;
+    ~InFile() { close(); }
+    bool open(const std::string &path);
+    void close();
+    bool ok() const { return f_ != nullptr; }
+    size_t read(void *dst, size_t n);                 // like fread(dst, 1, n)
+    bool getline(std::vector<char> &append_to);       // appends one line including its '\n'; false at end of input
+    static bool is_gz_name(const std::string &path) { return path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0; }
+
+private:
+    void *f_ = nullptr;                               // gzFile
 };
 
 class BlockReader {
@@ -33,7 +52,7 @@ public:
     // path2 empty = single-end.  block_bytes = SeqArcParam BlockSize (50 MiB by default).
     BlockReader(const std::string &path1, const std::string &path2, uint64_t block_bytes);
     ~BlockReader();
-    bool ok() const { return f_[0] != nullptr && (!pe_ || f_[1] != nullptr); }
+    bool ok() const { return f_[0].ok() && (!pe_ || f_[1].ok()); }
     bool pe() const { return pe_; }
     // next block of FASTQ text (cut exactly like the reference); false at end of input
     bool next_text(std::vector<char> &t1, std::vector<char> &t2);
@@ -42,14 +61,14 @@ public:
     static int get_end_pos(int len, const char *buf, int valid, const std::string &firstline);
 
 private:
-    FILE *f_[2] = {nullptr, nullptr};
+    InFile f_[2];
     bool pe_ = false, eof_ = false;
     uint64_t block_bytes_;
     std::string first_[2], left_[2];
     uint64_t off_[2] = {0, 0};
 };
 
-// FASTQ text -> MemBuf (SE: t2 empty).  Only plain "+" separator lines are supported.
+// FASTQ text -> MemBuf (SE: t2 empty).  '+' lines are either all bare or all "+<ID>" (MemBuf::comment).
 void parse_block(const std::vector<char> &t1, const std::vector<char> &t2, bool pe, MemBuf &mb);
 // inverse (recoverDataNoComment): MemBuf -> FASTQ text, PE de-interleaved
 void render_block(const MemBuf &mb, bool pe, std::string &o1, std::string &o2);

@@ -33,7 +33,7 @@ int sqh_cut_blocks(const char *p1, const char *p2, uint64_t block_bytes, uint32_
 // Write an archive from ready-made block records (concatenated in `recs`, lengths in `lens`).
 int sqh_write_arc(const char *path, int pe, int usemodel, int lossy, int md5, const char *name1, const char *name2,
                   const uint8_t *idbin, const uint8_t *model, uint64_t modellen, const uint8_t *recs, const uint64_t *lens,
-                  const uint64_t *src1, const uint64_t *src2, int nblocks, const uint8_t *ref_md5) {
+                  const uint64_t *src1, const uint64_t *src2, int nblocks, const uint8_t *ref_md5, int comment) {
     ArcWriter w;
     if (!w.open(path)) return -1;
     uint64_t o = 0, so[2] = {0, 0};
@@ -49,6 +49,7 @@ int sqh_write_arc(const char *path, int pe, int usemodel, int lossy, int md5, co
     if (idbin) memcpy(p.idbin, idbin, 512);
     if (model) p.model.assign(model, model + modellen);
     if (ref_md5) { p.has_ref = true; memcpy(p.ref_md5, ref_md5, 16); }     // archive written against a reference index
+    p.comment = comment != 0;                                              // '+' lines repeat the ID
     return w.finish(p) ? 0 : -1;
 }
 
@@ -57,13 +58,11 @@ int sqh_write_arc(const char *path, int pe, int usemodel, int lossy, int md5, co
 int sqh_analyse_ids(const char *p1, const char *p2, uint64_t block_bytes, uint8_t *idbin) {
     try {
         bool pe = p2 && *p2;
-        FILE *f1 = fopen(p1, "rb"), *f2 = pe ? fopen(p2, "rb") : nullptr;
-        if (!f1 || (pe && !f2)) return -1;
+        InFile f1, f2;
+        if (!f1.open(p1) || (pe && !f2.open(p2))) return -1;
         uint64_t quota = block_bytes / (pe ? 2 : 1);
-        char *line = nullptr;
-        size_t cap = 0;
-        auto record = [&](FILE *f, std::vector<char> &t) {
-            for (int k = 0; k < 4; k++) { ssize_t n = getline(&line, &cap, f); if (n <= 0) return false; t.insert(t.end(), line, line + n); }
+        auto record = [&](InFile &f, std::vector<char> &t) {
+            for (int k = 0; k < 4; k++) if (!f.getline(t)) return false;
             return true;
         };
         memset(idbin, 0, 512);
@@ -76,9 +75,6 @@ int sqh_analyse_ids(const char *p1, const char *p2, uint64_t block_bytes, uint8_
             parse_block(t1, t2, pe, mb);
             ok = analyse_id_bins(mb, pe, idbin);
         }
-        free(line);
-        fclose(f1);
-        if (f2) fclose(f2);
         return idbin[0];
     } catch (const std::exception &) {
         return -2;

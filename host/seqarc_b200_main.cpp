@@ -47,9 +47,11 @@ static void read_config(Opt &o) {
     fclose(f);
 }
 
-static std::string base_name(const std::string &p) {
+static std::string base_name(const std::string &p) {      // stored in trailer params 13 / 14, without a ".gz" suffix
     size_t k = p.find_last_of('/');
-    return k == std::string::npos ? p : p.substr(k + 1);
+    std::string b = k == std::string::npos ? p : p.substr(k + 1);
+    if (InFile::is_gz_name(b)) b.resize(b.size() - 3);
+    return b;
 }
 static uint64_t file_size(const std::string &p) {
     struct stat st;
@@ -83,20 +85,15 @@ static sq_block_in as_in(const MemBuf &m) {
 // reference with oracle/sizefake.c: 5 x 4298 reads of 244 B at BlockSize 1 MiB, single-end).
 static void sample_blocks(const Opt &o, std::vector<MemBuf> &out) {
     bool pe = !o.in2.empty();
-    FILE *f1 = fopen(o.in1.c_str(), "rb"), *f2 = pe ? fopen(o.in2.c_str(), "rb") : nullptr;
-    if (!f1 || (pe && !f2)) die("cannot open input");
+    InFile f1, f2;
+    if (!f1.open(o.in1) || (pe && !f2.open(o.in2))) die("cannot open input");
     // paired-end: BlockSize / 2 per mate file, the same number of records from both files
     // (measured: 5 x 1461 pairs of 359 B per mate at BlockSize 1 MiB)
     uint64_t quota = ((uint64_t)o.block_mb << 20) / (pe ? 2 : 1);
     std::vector<char> t1, t2;
-    char *line = nullptr;
-    size_t cap = 0;
-    auto record = [&](FILE *f, std::vector<char> &t) {
-        for (int k = 0; k < 4; k++) {
-            ssize_t n = getline(&line, &cap, f);
-            if (n <= 0) return false;
-            t.insert(t.end(), line, line + n);
-        }
+    auto record = [&](InFile &f, std::vector<char> &t) {
+        for (int k = 0; k < 4; k++)
+            if (!f.getline(t)) return false;
         return true;
     };
     for (int b = 0; b < 5; b++) {
@@ -109,9 +106,6 @@ static void sample_blocks(const Opt &o, std::vector<MemBuf> &out) {
         out.emplace_back();
         parse_block(t1, t2, pe, out.back());
     }
-    free(line);
-    fclose(f1);
-    if (f2) fclose(f2);
 }
 
 static int do_compress(const Opt &o) {
@@ -120,11 +114,16 @@ static int do_compress(const Opt &o) {
     bool pe = !o.in2.empty();
     uint64_t total = file_size(o.in1) + (pe ? file_size(o.in2) : 0);
     // doCheckSetEncodeOpt @0x408104-0x40831f: usemodel when total * 0.0023947358 > 33,693,269; off for Qlevel > 2
-    bool usemodel = (double)total * 0.0023947358 > 33693269.0 && o.qlevel <= 2;
+    // (single-precision arithmetic as in the binary; a .gz input's size is scaled by 2.73 first, constants @0x449948 / @0x449950)
+    bool gz = InFile::is_gz_name(o.in1);
+    long long est = (long long)((float)(long long)total * 0.0023947358f);
+    if (gz) est = (long long)((float)est * 2.73f);
+    bool usemodel = est > 33693269 && o.qlevel <= 2;
     if (getenv("SQ_FORCE_USEMODEL")) usemodel = atoi(getenv("SQ_FORCE_USEMODEL")) != 0;
     ArcParams ap;
     ap.pe = pe; ap.usemodel = usemodel; ap.lossy = o.lossy; ap.md5 = o.md5;
     ap.name1 = base_name(o.in1); ap.name2 = base_name(o.in2);
+    ap.gz = gz;
     if (!o.ref.empty()) {
         // A reference index turns on doAlignEncode @0x42d4c0.  Alignment itself is outside this path: every read is
         // coded as unmapped, which is what the reference writes when nothing maps ("Align block:0") -- same entropy
@@ -154,6 +153,7 @@ static int do_compress(const Opt &o) {
     bool okbins = true;
     for (auto &m : sample)
         if (okbins) okbins = analyse_id_bins(m, pe, ap.idbin);
+    ap.comment = !sample.empty() && sample[0].comment;
     if (o.verbose) fprintf(stderr, "bOrderBin %d petype %d\n", ap.idbin[0], ap.idbin[1]);
     sq_ctx *c = make_ctx(o, usemodel, o.lossy, o.lossy_r, o.md5, ap.idbin[0], ap.has_ref ? (pe ? 2 : 1) : 0);
     if (usemodel) {
@@ -178,6 +178,7 @@ static int do_compress(const Opt &o) {
         while ((int)mbs.size() < batch) {
             mbs.emplace_back();
             if (!rd.next(mbs.back())) { mbs.pop_back(); more = false; break; }
+            if (mbs.back().comment != ap.comment) die("'+' lines must be all bare or all a copy of the ID");
         }
         if (mbs.empty()) break;
         int n = (int)mbs.size();
@@ -287,6 +288,7 @@ static int do_decompress(const Opt &o) {
                     if (memcmp(dig, md5, 16) != 0) die("decode: Name md5 unequal");
                 }
             }
+            m.comment = ar.p.comment;
             render_block(m, pe, o1, o2);
             fwrite(o1.data(), 1, o1.size(), f1);
             if (pe) fwrite(o2.data(), 1, o2.size(), f2);

@@ -23,7 +23,11 @@ def case_fastq(name):
         return tuple(gzip.open(os.path.join(GOLD, "err_pe1000_%d.fq.gz" % k), "rb").read() for k in (1, 2))
     blk = sf.make_block(**m["src"])
     t = sf.to_fastq(blk)
-    return t if m["pe"] else (t,)
+    t = t if m["pe"] else (t,)
+    if m.get("plus"):       # '+' lines that repeat the ID
+        from tools.make_golden import plus_lines
+        t = tuple(plus_lines(x) for x in t)
+    return t
 
 
 def preprocess_sample(fastq, blocksize: int, max_blocks: int = 5, fastq2=None):

@@ -19,7 +19,9 @@ CLI = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
 IDENTICAL = ["err_pe1000", "err_pe1000_nomd5", "srr_pe100", "illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
              "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel", "illumina_pe150_usemodel",
              # BASELINE configs[4]: reference index given, nothing maps
-             "illumina_pe150_ref", "se100_q8_ref", "err_pe1000_ref", "illumina_pe150_ref_3blocks"]
+             "illumina_pe150_ref", "se100_q8_ref", "err_pe1000_ref", "illumina_pe150_ref_3blocks",
+             # "+<ID>" separator lines
+             "se100_q8_plus", "illumina_pe150_plus_3blocks"]
 
 
 def _setup(name, d):
@@ -64,6 +66,27 @@ def test_cli_archive_is_byte_identical_to_reference(name):
         arc = _compress(m, paths, d)
     assert len(arc) == m["arc_bytes"]
     assert hashlib.md5(arc).hexdigest() == m["arc_md5"]
+
+
+@pytest.mark.parametrize("name", ["err_pe1000", "illumina_pe150_3blocks", "se100_q8"])
+def test_cli_gzip_input_gives_the_reference_archive(name):
+    """.gz input: the reference writes the same archive as for the plain files except trailer param 4 = 1 (measured with
+    SeqArc-1.6 on err_pe1000 and the 3-block PE case; the stored names drop the .gz suffix)."""
+    import gzip
+    with tempfile.TemporaryDirectory() as d:
+        m, fq, paths = _setup(name, d)
+        gz = []
+        for p in paths:
+            with open(p + ".gz", "wb") as f:
+                with gzip.GzipFile(fileobj=f, mode="wb", mtime=0) as g:
+                    g.write(open(p, "rb").read())
+            os.remove(p)
+            gz.append(p + ".gz")
+        arc = _compress(m, gz, d)
+    want = common.case_archive(name)
+    k = want.rindex(b"\x84\x81\x00\x85\x81\x01")          # params 4 and 5 in the trailer
+    want = want[:k + 2] + b"\x01" + want[k + 3:]
+    assert arc == want
 
 
 @pytest.mark.parametrize("name", [c for c in common.CASES if "lossy" not in c])

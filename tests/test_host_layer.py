@@ -22,7 +22,7 @@ def hl():
     L.sqh_cut_blocks.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.sqh_write_arc.restype = C.c_int
     L.sqh_write_arc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p,
-                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
+                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     return L
 
 
@@ -34,6 +34,30 @@ def _write_inputs(name, d):
         open(p, "wb").write(t)
         paths.append(p)
     return paths
+
+
+@pytest.mark.parametrize("name", ["se100_q8_3blocks", "illumina_pe150_3blocks"])
+def test_block_cutter_reads_gzip_input(hl, name):
+    """The reference cuts a .gz input exactly like the plain file (measured: same records, same block index, only
+    trailer param 4 differs); so does the reader here."""
+    import gzip
+    m = common.MANIFEST[name]
+    bs = int((m["config"] or {}).get("BlockSize(M)", 50)) << 20
+    with tempfile.TemporaryDirectory() as d:
+        paths = _write_inputs(name, d)
+        gz = []
+        for p in paths:
+            with open(p + ".gz", "wb") as f:
+                with gzip.GzipFile(fileobj=f, mode="wb", mtime=0) as g:
+                    g.write(open(p, "rb").read())
+            gz.append(p + ".gz")
+        res = []
+        for ps in (paths, gz):
+            cap = 64
+            nr, s1, s2 = np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+            n = hl.sqh_cut_blocks(ps[0].encode(), ps[1].encode() if m["pe"] else None, bs, nr.ctypes.data, s1.ctypes.data, s2.ctypes.data, cap)
+            res.append((n, list(nr[:n]), list(s1[:n]), list(s2[:n])))
+    assert res[0][0] == 3 and res[0] == res[1]
 
 
 @pytest.mark.parametrize("name", ["se100_q8_3blocks", "illumina_pe150_3blocks", "se100_q8_usemodel", "illumina_pe150", "err_pe1000"])
@@ -83,7 +107,7 @@ def test_arc_writer_reproduces_reference_file(hl, name):
         r = hl.sqh_write_arc(out.encode(), int(m["pe"]), int(params[6][0]), int(params[16][0]), int(params[17][0]),
                              params[13], params.get(14, b""), idbin.ctypes.data, mb.ctypes.data if mb is not None else None,
                              0 if mb is None else mb.shape[0], ra.ctypes.data, lens.ctypes.data, s1.ctypes.data,
-                             s2.ctypes.data if s2 is not None else None, len(lens), arc["trailer"].get(8))
+                             s2.ctypes.data if s2 is not None else None, len(lens), arc["trailer"].get(8), int(params[2] == b"\x00"))
         assert r == 0
         got = open(out, "rb").read()
     assert got == data

@@ -53,6 +53,10 @@ CASES = [
     dict(name="err_pe1000_ref", src="err", pe=True, opts=[], config=None, ref=dict(n=2000000, seed=5)),
     dict(name="illumina_pe150_ref_3blocks", src=dict(kind="illumina_pe150", n_templates=3200, seed=31), pe=True, opts=[],
          config={"BlockSize(M)": 1}, ref=dict(n=2000000, seed=5)),
+    # '+' lines that repeat the ID: same block records, trailer param 2 = 0 (and 0 instead of 1 in the SE index records)
+    dict(name="se100_q8_plus", src=dict(kind="se100_q8", n_templates=4000, seed=12345), pe=False, opts=[], config=None, plus=True),
+    dict(name="illumina_pe150_plus_3blocks", src=dict(kind="illumina_pe150", n_templates=3200, seed=31), pe=True, opts=[],
+         config={"BlockSize(M)": 1}, plus=True),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
@@ -64,7 +68,16 @@ def case_fastq(case):
         return tuple(gzip.open(os.path.join(GOLD, "err_pe1000_%d.fq.gz" % k), "rb").read() for k in (1, 2))
     blk = sf.make_block(**case["src"])
     t = sf.to_fastq(blk)
-    return t if case["pe"] else (t,)
+    t = t if case["pe"] else (t,)
+    return tuple(plus_lines(x) for x in t) if case.get("plus") else t
+
+
+def plus_lines(text):
+    """Rewrite every bare '+' line as '+<ID>'."""
+    lines = text.split(b"\n")
+    for i in range(2, len(lines) - 1, 4):
+        lines[i] = b"+" + lines[i - 2][1:]
+    return b"\n".join(lines)
 
 
 def random_reference(n, seed):
@@ -126,6 +139,8 @@ def main():
                          fastq_md5=[hashlib.md5(t).hexdigest() for t in fq])
             if ref_md5:
                 entry.update(ref=case["ref"], ref_md5=ref_md5)
+            if case.get("plus"):
+                entry.update(plus=True)
             if case.get("fake_size"):
                 from oracle import arcwalk
                 assert "usemodel=1" in log, log[-1500:]
