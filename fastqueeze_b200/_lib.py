@@ -40,7 +40,8 @@ class SqBlockOut(C.Structure):
 class SqBlockDec(C.Structure):
     _fields_ = [("ids", C.c_void_p), ("idcap", C.c_uint64), ("seq", C.c_void_p), ("qual", C.c_void_p),
                 ("seqcap", C.c_uint64), ("idlen", C.c_void_p), ("seqlen", C.c_void_p), ("readcap", C.c_uint32),
-                ("nreads", C.c_uint32), ("idbytes", C.c_uint64), ("seqbytes", C.c_uint64), ("status", C.c_int32)]
+                ("nreads", C.c_uint32), ("idbytes", C.c_uint64), ("seqbytes", C.c_uint64), ("status", C.c_int32),
+                ("longflag", C.c_int32)]
 
 
 class SeqArcB200Error(RuntimeError):

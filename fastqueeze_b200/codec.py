@@ -32,6 +32,12 @@ class SeqArcMemBuf:
     def nreads(self):
         return int(self.seqlen.shape[0])
 
+    @property
+    def longflag(self):
+        """membuf+0x2: a read longer than 65,535 bases (the Len stream then carries four length bytes and the
+        archive's block index records the flag in bit 0 of the length field)."""
+        return int(self.seqlen.shape[0] > 0 and int(np.max(self.seqlen)) > 65535)
+
 
 @dataclass
 class SeqArcParam:
@@ -116,6 +122,7 @@ class EncapFqzComp:
             idlen, seqlen = _c(m.idlen, np.uint16), _c(m.seqlen, np.int32)
             keep.append((ids, seq, qual, idlen, seqlen))
             ins[i].nreads = seqlen.shape[0]
+            ins[i].longflag = m.longflag
             ins[i].ids, ins[i].seq, ins[i].qual = ids.ctypes.data, seq.ctypes.data, qual.ctypes.data
             ins[i].idlen, ins[i].seqlen = idlen.ctypes.data, seqlen.ctypes.data
             ins[i].idbytes, ins[i].seqbytes = ids.shape[0], seq.shape[0]
@@ -149,6 +156,7 @@ class EncapFqzComp:
             ob = np.empty(cap, dtype=np.uint8)
             keep.append((ids, seq, qual, idlen, seqlen, ob))
             ins[i].nreads = seqlen.shape[0]
+            ins[i].longflag = m.longflag
             ins[i].ids, ins[i].seq, ins[i].qual = ids.ctypes.data, seq.ctypes.data, qual.ctypes.data
             ins[i].idlen, ins[i].seqlen = idlen.ctypes.data, seqlen.ctypes.data
             ins[i].idbytes, ins[i].seqbytes = ids.shape[0], seq.shape[0]
@@ -165,7 +173,8 @@ class EncapFqzComp:
         return lens
 
     # doDecode @0x42eb60 over a batch of block records; returns SeqArcMemBuf list
-    def doDecode(self, records, dbg: DebugInfo = None, idcap=None, seqcap=None, readcap=None, raise_on_error=True):
+    def doDecode(self, records, dbg: DebugInfo = None, idcap=None, seqcap=None, readcap=None, raise_on_error=True,
+                 longflags=None):
         n = len(records)
         recs = (C.c_void_p * n)()
         lens = (C.c_uint64 * n)()
@@ -184,6 +193,7 @@ class EncapFqzComp:
             decs[i].ids, decs[i].idcap = bufs[0].ctypes.data, ic
             decs[i].seq, decs[i].qual, decs[i].seqcap = bufs[1].ctypes.data, bufs[2].ctypes.data, sc
             decs[i].idlen, decs[i].seqlen, decs[i].readcap = bufs[3].ctypes.data, bufs[4].ctypes.data, rcap
+            decs[i].longflag = int(longflags[i]) if longflags is not None else 0
         r = self._L.sq_decode_blocks(self._h, recs, lens, n, decs)
         self._debug(dbg)
         res = []

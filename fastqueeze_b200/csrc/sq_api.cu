@@ -207,7 +207,7 @@ BlkCost block_cost(const sq_ctx *c, const sq_block_in &b, bool host) {
     k.eb[ST_NAME] = c->p.id_rule ? 0 : b.idbytes + 3 * n;
     k.obuf = 0;
     for (int s = 0; s < ST_COUNT; s++) k.obuf += al16(k.eb[s] + k.eb[s] / 2 + 256);
-    k.side = al16(24 * n + b.seqbytes + 4096);
+    k.side = al16(28 * n + b.seqbytes + 4096);
     k.rec = al16(256 + b.idbytes + 2 * b.seqbytes + 8 * n);
     return k;
 }
@@ -278,6 +278,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
         BlockDesc &d = bd[i];
         memset(&d, 0, sizeof d);
         d.nreads = b.nreads; d.idbytes = b.idbytes; d.seqbytes = b.seqbytes;
+        d.longflag = b.longflag ? 1 : 0;
         d.rbase = (u32)R;
         rbase[i] = (u32)R;
         R += b.nreads;
@@ -479,7 +480,6 @@ int encode_blocks(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out
     if (!c || !blocks || !out || n <= 0) { if (c) c->err = "bad argument"; return SQ_ERR_ARG; }
     CUDA_OK(c, cudaSetDevice(c->p.device));
     for (int i = 0; i < n; i++) {
-        if (blocks[i].longflag) { c->err = "long-read blocks (encode_len_long @0x422e70) are not supported"; return SQ_ERR_ARG; }
         if (blocks[i].seqbytes >= (1ull << 31) || blocks[i].idbytes >= (1ull << 31)) { c->err = "block too large"; return SQ_ERR_ARG; }
         if (blocks[i].nreads && (!blocks[i].idlen || !blocks[i].seqlen)) { c->err = "null length array"; return SQ_ERR_ARG; }
     }
@@ -719,6 +719,7 @@ int decode_wave(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_
         DecBlock &d = db[i];
         sq_block_dec &o = out[i];
         d.idcap = o.idcap; d.seqcap = o.seqcap; d.readcap = o.readcap;
+        d.longflag = o.longflag ? 1 : 0;
         if (d.status) continue;
         if (host) {
             d.rec = (u8 *)need(A.take(reclens[i] + 16));

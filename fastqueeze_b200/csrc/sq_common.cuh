@@ -44,6 +44,7 @@ struct BlockDesc {
     const i32 *seqlen;                // +0xd0
     u8 *qual_work;                    // qualities the coder sees (= qual, or the R-Block smoothed copy)
     u32 nreads;
+    i32 longflag;                     // membuf+0x2: the block holds a read > 65,535 bases (compressLen_long @0x423710)
     u32 rbase;                        // first read of this block in the wave-wide per-read arrays
     u64 idbytes, seqbytes;
     u64 ebase[ST_COUNT];              // first element of this block in the element / triple arrays

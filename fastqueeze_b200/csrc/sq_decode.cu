@@ -298,7 +298,7 @@ SQ_D u32 wm_decode(u32 *mp, RcDecW &rc, int lane, u64 pol) {
 // Len stream (decompressLen_short @0x428170 / decode_len_short @0x427ca0) + read offsets.
 // The reference keeps last_len across blocks per decoder instance; a zero-length
 // read therefore decodes to "whatever came before".  Here last_len starts at 0 for every block.
-struct LenSmem { SmModel<256> len1, len2; SmModel<2> same; };
+struct LenSmem { SmModel<256> len1, len2, len3, len4; SmModel<2> same; };
 __global__ void __launch_bounds__(32) k_dec_len(DecBlock *db) {
     __shared__ LenSmem sm;
     DecBlock &d = db[blockIdx.x];
@@ -308,12 +308,16 @@ __global__ void __launch_bounds__(32) k_dec_len(DecBlock *db) {
     RcDec rc;
     rc.start(d.rec + d.off[4], d.rec + d.off[4] + d.len[4]);
     sm.len1.init(); sm.len2.init(); sm.same.init();
+    const bool lng = d.longflag != 0;                 // decode_len_long @0x427190: four length bytes
+    if (lng) { sm.len3.init(); sm.len4.init(); }
     i32 last = 0;
     u64 tot = 0;
     for (u32 r = 0; r < d.nreads; r++) {
         if (sm.same.decode(rc) == 0) {
             u32 l1 = sm.len1.decode(rc), l2 = sm.len2.decode(rc);
-            last = (i32)(l1 | (l2 << 8));
+            u32 l3 = lng ? sm.len3.decode(rc) : 0, l4 = lng ? sm.len4.decode(rc) : 0;
+            last = (i32)(l1 | (l2 << 8) | (l3 << 16) | (l4 << 24));
+            if (last < 0) { d.status = SQ_ERR_FORMAT_K; return; }
         }
         d.seqlen[r] = last;
         d.seqoff[r] = (u32)tot;

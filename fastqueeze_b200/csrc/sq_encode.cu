@@ -45,7 +45,7 @@ __global__ void k_read_prep(const BlockDesc *bd, BlockState *bs, const u32 *rbas
     u32 r = w - rbase[b];
     i32 sl = bd[b].seqlen[r];
     u32 il = bd[b].idlen[r];
-    if (sl < 0 || sl > 65535 || il > 255) { bs[b].status = SQ_ERR_INPUT_K; sl = 0; il = 0; }
+    if (sl < 0 || (sl > 65535 && !bd[b].longflag) || il > 255) { bs[b].status = SQ_ERR_INPUT_K; sl = 0; il = 0; }
     seqoff[w] = (u32)sl;
     idoff[w] = il;
 }
@@ -818,8 +818,10 @@ struct KModel {
         for (int i = 0; i < n; i++) bits[i].encode(rc, (v >> i) & 1);
     }
 };
+// bytes of side scratch reserved for the Len stream: 2 B per coded symbol, 3 (5 for long-read blocks) symbols per read
+SQ_D u64 len_region(const BlockDesc &d) { return (d.longflag ? 10ull : 6ull) * d.nreads + 16; }
 struct SideSmem {
-    SmModel<256> len1, len2;
+    SmModel<256> len1, len2, len3, len4;
     SmModel<2> same, tip;
     SmModel<11> ch;
     SmModel<95> maxq;
@@ -841,7 +843,7 @@ __global__ void __launch_bounds__(160) k_side(const BlockDesc *bd, BlockState *b
         // symbol); Ch gets 1 B per non-ACGT base (an 11-symbol alphabet needs < 0.5 B), Pos the rest
         // (>= 1 B per candidate base).  Overflow is detected by the coder, never assumed away.
         u64 o = 0;
-        sm.off[0] = o; o += 6ull * n + 16;
+        sm.off[0] = o; o += len_region(d);
         sm.off[1] = o; o += 2ull * n + 16;
         sm.off[2] = o; o += (u64)nch + 64;
         sm.off[3] = o; o += 2ull * nf + 16;
@@ -860,11 +862,15 @@ __global__ void __launch_bounds__(160) k_side(const BlockDesc *bd, BlockState *b
     if (wid == 0) {                                             // Len
         rc.start(base + sm.off[0], base + sm.off[1]);
         sm.len1.init(); sm.len2.init(); sm.same.init();
+        const bool lng = d.longflag != 0;                       // compressLen_long @0x423710: four length bytes
+        if (lng) { sm.len3.init(); sm.len4.init(); }
         for (u32 r = 0; r < n; r++) {
             i32 len = d.seqlen[r];
             // the encoder compares with this+0x1060, which it never writes (ctor value 0): SURVEY 8a quirk
-            if (len != 0) { sm.same.encode(rc, 0); sm.len1.encode(rc, len & 0xff); sm.len2.encode(rc, (len >> 8) & 0xff); }
-            else sm.same.encode(rc, 1);
+            if (len != 0) {
+                sm.same.encode(rc, 0); sm.len1.encode(rc, len & 0xff); sm.len2.encode(rc, (len >> 8) & 0xff);
+                if (lng) { sm.len3.encode(rc, (len >> 16) & 0xff); sm.len4.encode(rc, ((u32)len >> 24) & 0xff); }
+            } else sm.same.encode(rc, 1);
         }
         rc.finish();
         bs[b].side_len[0] = (u32)(rc.out - (base + sm.off[0])); bs[b].side_cnt[0] = n; ovf = rc.overflow;
@@ -1076,7 +1082,7 @@ __global__ void __launch_bounds__(256) k_pack(const BlockDesc *bd, const BlockSt
     }
     // Dege streams (tags 23, 14, 24, 25, 26): u32le count + range-coder bytes, omitted when empty
     {
-        u64 o = 6ull * d.nreads + 16;                              // region offsets as laid out by k_side
+        u64 o = len_region(d);                                     // region offsets as laid out by k_side
         u32 nch = (u32)d.seqbytes - s.acgt, nf = s.side_cnt[3];
         u64 offs[6] = {0, o, o + 2ull * d.nreads + 16, 0, 0, 0};
         offs[3] = offs[2] + (u64)nch + 64;

@@ -69,6 +69,7 @@ struct DecBlock {
     u8 *ids, *seq, *qual; u16 *idlen; i32 *seqlen;
     u64 idcap, seqcap; u32 readcap;
     u32 nreads;
+    i32 longflag;                       // from the archive's block index: Len stream written by compressLen_long
     // per-block model tables (device workspace)
     u8 *seqtab; u32 *qualtab; u32 *nametab;
     // dege arrays

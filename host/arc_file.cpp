@@ -30,9 +30,10 @@ bool ArcWriter::open(const std::string &path) {
     return true;
 }
 
-void ArcWriter::add_block(const uint8_t *rec, uint64_t len, const uint64_t sb[2], const uint64_t so[2]) {
+void ArcWriter::add_block(const uint8_t *rec, uint64_t len, const uint64_t sb[2], const uint64_t so[2], bool longflag) {
     BlockIndex b;
     b.len = (uint32_t)len;
+    b.longflag = longflag;
     b.src_bytes[0] = (uint32_t)sb[0]; b.src_bytes[1] = (uint32_t)sb[1];
     b.arc_off = off_;
     b.src_off[0] = so[0]; b.src_off[1] = so[1];
@@ -76,7 +77,7 @@ bool ArcWriter::finish(const ArcParams &p) {
     }
     std::vector<uint8_t> ix;
     for (auto &b : idx_) {
-        le(ix, (uint64_t)b.len * 2, 4);                  // low bit: long-read flag
+        le(ix, (uint64_t)b.len * 2 + (b.longflag ? 1 : 0), 4);    // low bit: long-read flag
         if (p.pe) { le(ix, b.src_bytes[0], 4); le(ix, b.src_bytes[1], 4); }
         else { le(ix, p.comment ? 0 : 1, 4); le(ix, b.src_bytes[0], 4); }
         le(ix, 0, 4);
@@ -172,6 +173,7 @@ bool ArcReader::load(const std::string &path) {
         const uint8_t *x = ix.data() + o;
         BlockIndex b;
         b.len = (uint32_t)(rd(x, 4) >> 1);
+        b.longflag = rd(x, 4) & 1;
         if (p.pe) { b.src_bytes[0] = (uint32_t)rd(x + 4, 4); b.src_bytes[1] = (uint32_t)rd(x + 8, 4); }
         else b.src_bytes[0] = (uint32_t)rd(x + 8, 4);
         b.arc_off = rd(x + 16, 8);

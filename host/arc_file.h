@@ -27,6 +27,7 @@ struct ArcParams {
 
 struct BlockIndex {                // one record of trailer TAG 7 (32 B single-end, 40 B paired-end)
     uint32_t len = 0;              // bytes of the block record
+    bool longflag = false;         // bit 0 of the index length field: the block holds a read > 65,535 bases
     uint32_t src_bytes[2] = {0, 0};
     uint64_t arc_off = 0;          // offset of the record in the .arc (first one: 16)
     uint64_t src_off[2] = {0, 0};
@@ -36,7 +37,7 @@ class ArcWriter {
 public:
     bool open(const std::string &path);
     // append one block record (already "tag 1 | size(4) | streams"); records must come in block order
-    void add_block(const uint8_t *rec, uint64_t len, const uint64_t src_bytes[2], const uint64_t src_off[2]);
+    void add_block(const uint8_t *rec, uint64_t len, const uint64_t src_bytes[2], const uint64_t src_off[2], bool longflag = false);
     bool finish(const ArcParams &p);
     uint64_t bytes() const { return off_; }
 

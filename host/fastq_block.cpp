@@ -151,6 +151,7 @@ void parse_block(const std::vector<char> &t1, const std::vector<char> &t2, bool 
     mb.seq.reserve((t1.size() + t2.size()) / 2);
     mb.qual.reserve((t1.size() + t2.size()) / 2);
     mb.comment = nrec && ll[0][2] > 1;
+    mb.longflag = false;
     for (size_t r = 0; r < nrec; r++) {
         for (int k = 0; k < (pe ? 2 : 1); k++) {
             const char *id = ln[k][4 * r], *sq = ln[k][4 * r + 1], *pl = ln[k][4 * r + 2], *ql = ln[k][4 * r + 3];
@@ -166,6 +167,7 @@ void parse_block(const std::vector<char> &t1, const std::vector<char> &t2, bool 
             mb.qual.insert(mb.qual.end(), ql, ql + qll);
             mb.idlen.push_back((uint16_t)(il - 1));
             mb.seqlen.push_back(sl);
+            if (sl > 65535) mb.longflag = true;
         }
     }
 }

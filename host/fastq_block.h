@@ -25,6 +25,7 @@ struct MemBuf {
     std::vector<int32_t> seqlen;
     uint64_t src_bytes[2] = {0, 0};     // FASTQ bytes this block took from file 1 / file 2
     uint64_t src_off[2] = {0, 0};       // their offsets in the source files
+    bool longflag = false;              // membuf+0x2: a read longer than 65,535 bases (Len stream with four length bytes)
     bool comment = false;               // the '+' lines repeat the ID (trailer param 2 = 0); decided by the block's first record
     uint32_t nreads() const { return (uint32_t)seqlen.size(); }
 };

@@ -33,13 +33,13 @@ int sqh_cut_blocks(const char *p1, const char *p2, uint64_t block_bytes, uint32_
 // Write an archive from ready-made block records (concatenated in `recs`, lengths in `lens`).
 int sqh_write_arc(const char *path, int pe, int usemodel, int lossy, int md5, const char *name1, const char *name2,
                   const uint8_t *idbin, const uint8_t *model, uint64_t modellen, const uint8_t *recs, const uint64_t *lens,
-                  const uint64_t *src1, const uint64_t *src2, int nblocks, const uint8_t *ref_md5, int comment) {
+                  const uint64_t *src1, const uint64_t *src2, int nblocks, const uint8_t *ref_md5, int comment, const uint8_t *longflags) {
     ArcWriter w;
     if (!w.open(path)) return -1;
     uint64_t o = 0, so[2] = {0, 0};
     for (int i = 0; i < nblocks; i++) {
         uint64_t sb[2] = {src1[i], src2 ? src2[i] : 0};
-        w.add_block(recs + o, lens[i], sb, so);
+        w.add_block(recs + o, lens[i], sb, so, longflags && longflags[i]);
         o += lens[i];
         so[0] += sb[0]; so[1] += sb[1];
     }

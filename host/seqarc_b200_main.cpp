@@ -74,6 +74,7 @@ static sq_ctx *make_ctx(const Opt &o, bool usemodel, bool lossy, double r, bool 
 static sq_block_in as_in(const MemBuf &m) {
     sq_block_in b{};
     b.nreads = m.nreads();
+    b.longflag = m.longflag;
     b.ids = m.ids.data(); b.seq = m.seq.data(); b.qual = m.qual.data();
     b.idlen = m.idlen.data(); b.seqlen = m.seqlen.data();
     b.idbytes = m.ids.size(); b.seqbytes = m.seq.size();
@@ -193,7 +194,7 @@ static int do_compress(const Opt &o) {
         int rc = sq_encode_blocks(c, in.data(), n, out.data());
         if (rc != SQ_OK) die(std::string("encode: ") + sq_last_error(c) + " (status " + std::to_string(rc) + ")");
         for (int i = 0; i < n; i++) {
-            wr.add_block(recs[i].data(), out[i].len, mbs[i].src_bytes, mbs[i].src_off);
+            wr.add_block(recs[i].data(), out[i].len, mbs[i].src_bytes, mbs[i].src_off, mbs[i].longflag);
             in_bytes += mbs[i].src_bytes[0] + mbs[i].src_bytes[1];
         }
         nblocks += n;
@@ -266,7 +267,8 @@ static int do_decompress(const Opt &o) {
             m.ids.resize(src + 64); m.seq.resize(src / 2 + 64); m.qual.resize(src / 2 + 64);
             uint32_t rcap = (uint32_t)(src / 6 + 16);
             m.idlen.resize(rcap); m.seqlen.resize(rcap);
-            dec[i] = {m.ids.data(), m.ids.size(), m.seq.data(), m.qual.data(), m.seq.size(), m.idlen.data(), m.seqlen.data(), rcap, 0, 0, 0, 0};
+            dec[i] = {m.ids.data(), m.ids.size(), m.seq.data(), m.qual.data(), m.seq.size(), m.idlen.data(), m.seqlen.data(), rcap, 0, 0, 0, 0,
+                      bi.longflag ? 1 : 0};
         }
         int rc = sq_decode_blocks(c, recs.data(), lens.data(), n, dec.data());
         if (rc != SQ_OK) {

@@ -62,7 +62,8 @@ typedef struct {
  * without separators, PE interleaved R1,R2,R1,R2 (getBlockReadPE @0x412920). */
 typedef struct {
     uint32_t nreads;          /* membuf+0x4  */
-    int32_t  longflag;        /* membuf+0x2  (reads > 65535 bp; not supported: SQ_ERR_ARG) */
+    int32_t  longflag;        /* membuf+0x2: set when the block holds a read longer than 65,535 bases; the Len stream is then
+                                 written by compressLen_long @0x423710 and the block-index length field carries bit 0 */
     const uint8_t  *ids;      /* membuf+0x80: IDs without '@' */
     const uint8_t  *seq;      /* membuf+0x88 */
     const uint8_t  *qual;     /* membuf+0x90 */
@@ -87,6 +88,7 @@ typedef struct {
     uint32_t nreads;          /* out */
     uint64_t idbytes, seqbytes;   /* out */
     int32_t  status;          /* out */
+    int32_t  longflag;        /* in: bit 0 of the block's length field in the archive index (decode_len_long @0x427190) */
 } sq_block_dec;
 
 typedef struct sq_ctx sq_ctx;

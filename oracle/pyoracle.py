@@ -42,10 +42,15 @@ class Block:
     def nreads(self):
         return int(self.seqlen.shape[0])
 
-    def cblock(self):
+    @property
+    def longflag(self):
+        """membuf+0x2: the block holds a read longer than 65,535 bases (measured: 65,536 sets it, 65,535 does not)."""
+        return int(self.seqlen.shape[0] > 0 and int(self.seqlen.max()) > 65535)
+
+    def cblock(self, longflag=None):
         b = CBlock()
         b.nreads = self.nreads
-        b.longflag = 0
+        b.longflag = self.longflag if longflag is None else int(longflag)
         self._keep = [np.ascontiguousarray(a) for a in (self.ids, self.seq, self.qual, self.idlen, self.seqlen)]
         b.ids, b.seq, b.qual, b.idlen, b.seqlen = [a.ctypes.data for a in self._keep]
         b.idbytes = int(self.ids.shape[0])
@@ -153,14 +158,14 @@ class Oracle:
         assert got == n
         return buf.tobytes()
 
-    def decode_block(self, rec: bytes, idcap=None, seqcap=None, readcap=None) -> Block:
+    def decode_block(self, rec: bytes, idcap=None, seqcap=None, readcap=None, longflag=0) -> Block:
         rec_a = np.frombuffer(rec, dtype=np.uint8)
         seqcap = seqcap or (64 << 20)
         idcap = idcap or (64 << 20)
         readcap = readcap or (1 << 22)
         blk = Block(np.zeros(idcap, np.uint8), np.zeros(readcap, np.uint16), np.zeros(seqcap, np.uint8),
                     np.zeros(seqcap, np.uint8), np.zeros(readcap, np.int32))
-        cb = blk.cblock()
+        cb = blk.cblock(longflag=longflag)        # the flag travels in the archive's block index, not in the record
         n = lib().sqo_decode_block(self.h, rec_a.ctypes.data, len(rec), C.byref(cb), idcap, seqcap, readcap)
         if n < 0:
             raise RuntimeError("oracle decode failed: %d" % n)

@@ -159,7 +159,7 @@ struct sqo_ctx {
     uint32_t *qual;         /* this+0x1500: SIMPLE_MODEL<95>[nqual] */
     uint32_t *name_prefix, *name_suffix, *name_len;   /* SIMPLE_MODEL<256>[256] x3 */
     uint32_t *name_middle;                            /* SIMPLE_MODEL<128>[8192] */
-    uint32_t len1[SM_STRIDE(256)], len2[SM_STRIDE(256)], same_len[SM_STRIDE(2)];
+    uint32_t len1[SM_STRIDE(256)], len2[SM_STRIDE(256)], len3[SM_STRIDE(256)], len4[SM_STRIDE(256)], same_len[SM_STRIDE(2)];
     int32_t last_len;       /* this+0x1060: only the decoders write it */
     uint8_t last_name[1024];
     int32_t lnl, lpl, lsl;  /* this+0x1488/0x148c/0x1490 */
@@ -263,16 +263,24 @@ static void reset_qual_models(sqo_ctx *c) {     /* compressQual @0x426f10-0x426f
 }
 
 /* ------------------------------------------------------------------ Len stream
- * compressLen @0x424120, compressLen_short @0x423f50, encode_len_short @0x4239a0. */
+ * compressLen @0x424120, compressLen_short @0x423f50, encode_len_short @0x4239a0.  A block holding a read
+ * longer than 65,535 bases (membuf+0x2, low bit of the block-index length field) goes through
+ * compressLen_long @0x423710 / encode_len_long @0x422e70: four length bytes with four SIMPLE_MODEL<256>
+ * (this+0x8, +0x418, +0x828, +0xc38), the same "last_len is never written" comparison. */
 int64_t sqo_stream_len(sqo_ctx *c, const sqo_block *b, uint8_t *out) {
     RC rc; rc_start_enc(&rc, out);
     sm_init(c->len1, 256); sm_init(c->len2, 256); sm_init(c->same_len, 2);
+    if (b->longflag) { sm_init(c->len3, 256); sm_init(c->len4, 256); }
     for (uint32_t i = 0; i < b->nreads; i++) {
         int32_t len = b->seqlen[i];
         if (len != 0) {   /* cmp with this+0x1060, which the encoder never writes (ctor value 0) */
             sm_encode(c->same_len, &rc, 0);
             sm_encode(c->len1, &rc, len & 0xff);
             sm_encode(c->len2, &rc, (len >> 8) & 0xff);
+            if (b->longflag) {
+                sm_encode(c->len3, &rc, (len >> 16) & 0xff);
+                sm_encode(c->len4, &rc, ((uint32_t)len >> 24) & 0xff);
+            }
         } else {
             sm_encode(c->same_len, &rc, 1);
         }

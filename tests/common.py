@@ -127,6 +127,7 @@ def case_blocks(name):
             e = idx[i + 1]["offs"][1] if i + 1 < nb else len(fq[0])
             parts = (fq[0][s:e],)
         blk = po.block_from_fastq(*parts)
+        assert idx[i]["long"] == blk.longflag          # bit 0 of the index length field: a read > 65,535 bases
         out.append((blk, b["raw"]))
     return kw, out
 

@@ -21,7 +21,9 @@ IDENTICAL = ["err_pe1000", "err_pe1000_nomd5", "srr_pe100", "illumina_pe150", "i
              # BASELINE configs[4]: reference index given, nothing maps
              "illumina_pe150_ref", "se100_q8_ref", "err_pe1000_ref", "illumina_pe150_ref_3blocks",
              # "+<ID>" separator lines
-             "se100_q8_plus", "illumina_pe150_plus_3blocks"]
+             "se100_q8_plus", "illumina_pe150_plus_3blocks",
+             # reads longer than 65,535 bases (compressLen_long, long flag in the block index)
+             "long_se"]
 
 
 def _setup(name, d):

@@ -51,7 +51,7 @@ def check(fq, blocks, roundtrip=True, **kw):
     for b, m in zip(blocks, mbs):
         assert m.status == 0
         assert m.out == o.encode_block(b)
-    back = codec.doDecode([m.out for m in mbs]) if roundtrip else []
+    back = codec.doDecode([m.out for m in mbs], longflags=[b.longflag for b in blocks]) if roundtrip else []
     for b, d in zip(blocks, back):
         want_q = po.rblock(b.qual, params["lossy_r"]) if params["lossy"] else b.qual
         assert d.status == 0
@@ -84,6 +84,22 @@ def test_degenerate_blocks(fq):
     check(fq, [one, all_n, homopolymer])
     empty_reads = po.block_from_records([(b"a", b"", b""), (b"b", b"", b""), (b"", b"ACGT", b"!!!!")])
     check(fq, [empty_reads], roundtrip=False)
+
+
+def test_long_reads(fq):
+    """Reads beyond 65,535 bases switch the block to compressLen_long (four length bytes); mixed with short, empty-tailed
+    and N-carrying reads, next to an ordinary block in the same call."""
+    rng = np.random.default_rng(77)
+    recs = []
+    for i, n in enumerate([70001, 12, 65536, 300, 131075]):
+        s = np.frombuffer(b"ACGTN", np.uint8)[rng.choice(5, n, p=[.2495, .2495, .2495, .2495, .002])].tobytes()
+        q = bytearray((np.clip(np.rint(rng.normal(25, 8, n)), 2, 40).astype(np.uint8) + 33).tobytes())
+        if i == 0:
+            q[-500:] = b"#" * 500
+        recs.append((b"long.%d length=%d" % (i, n), s, bytes(q)))
+    long_blk = po.block_from_records(recs)
+    assert long_blk.longflag == 1 and ragged_block(5, 200).longflag == 0
+    check(fq, [long_blk, ragged_block(5, 200)])
 
 
 def test_waves_give_identical_records(fq):

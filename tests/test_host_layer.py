@@ -22,7 +22,7 @@ def hl():
     L.sqh_cut_blocks.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.sqh_write_arc.restype = C.c_int
     L.sqh_write_arc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p,
-                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p]
     return L
 
 
@@ -107,7 +107,8 @@ def test_arc_writer_reproduces_reference_file(hl, name):
         r = hl.sqh_write_arc(out.encode(), int(m["pe"]), int(params[6][0]), int(params[16][0]), int(params[17][0]),
                              params[13], params.get(14, b""), idbin.ctypes.data, mb.ctypes.data if mb is not None else None,
                              0 if mb is None else mb.shape[0], ra.ctypes.data, lens.ctypes.data, s1.ctypes.data,
-                             s2.ctypes.data if s2 is not None else None, len(lens), arc["trailer"].get(8), int(params[2] == b"\x00"))
+                             s2.ctypes.data if s2 is not None else None, len(lens), arc["trailer"].get(8), int(params[2] == b"\x00"),
+                             bytes(r["long"] for r in idx))
         assert r == 0
         got = open(out, "rb").read()
     assert got == data

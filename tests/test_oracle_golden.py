@@ -36,7 +36,7 @@ def test_oracle_decode_reference_records(name):
         pytest.skip("rule-based ID regeneration (IDProcess::decodeIDS) is a 'next' row")
     o = po.Oracle(**kw)
     for blk, ref in blocks:
-        d = o.decode_block(ref)
+        d = o.decode_block(ref, longflag=blk.longflag)
         assert np.array_equal(d.seqlen, blk.seqlen)
         assert d.seq.tobytes() == blk.seq.tobytes()
         assert d.qual.tobytes() == blk.qual.tobytes()

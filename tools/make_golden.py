@@ -57,6 +57,8 @@ CASES = [
     dict(name="se100_q8_plus", src=dict(kind="se100_q8", n_templates=4000, seed=12345), pe=False, opts=[], config=None, plus=True),
     dict(name="illumina_pe150_plus_3blocks", src=dict(kind="illumina_pe150", n_templates=3200, seed=31), pe=True, opts=[],
          config={"BlockSize(M)": 1}, plus=True),
+    # reads longer than 65,535 bases: compressLen_long @0x423710 and the long flag in the block index
+    dict(name="long_se", src=dict(kind="long_se", n_templates=4, seed=9), pe=False, opts=[], config=None),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]

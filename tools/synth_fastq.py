@@ -60,6 +60,13 @@ def make_block(kind="illumina_pe150", n_templates=1000, seed=7, first=0, n_rate=
     hash_tail: fraction of reads whose quality ends in a run of '#' (exercises symbol 94).
     """
     rng = np.random.default_rng(seed)
+    if kind == "long_se":           # a few long reads (> 65,535 bases: encode_len_long), lengths fixed, n_templates <= 5
+        lens = [65536, 300, 70001, 1200, 66000][:n_templates]
+        idl = [b"read%d len=%d" % (first + i, n) for i, n in enumerate(lens)]
+        tot = sum(lens)
+        return dict(ids=np.frombuffer(b"".join(idl), dtype=np.uint8).copy(), idlen=np.array([len(x) for x in idl], np.uint16),
+                    seq=BASES[rng.integers(0, 4, tot)], qual=(np.clip(np.rint(rng.normal(20, 6, tot)), 2, 40).astype(np.uint8) + 33),
+                    seqlen=np.array(lens, np.int32), pe=False)
     pe = kind != "se100_q8"
     L = 150 if kind == "illumina_pe150" else 100
     n = n_templates * (2 if pe else 1)
