@@ -32,16 +32,19 @@ def test_oracle_encode_matches_reference(name):
 @pytest.mark.parametrize("name", [c for c in common.CASES if "lossy" not in c])
 def test_oracle_decode_reference_records(name):
     kw, blocks = common.case_blocks(name)
-    if kw["id_rule"]:
-        pytest.skip("rule-based ID regeneration (IDProcess::decodeIDS) is a 'next' row")
     o = po.Oracle(**kw)
     for blk, ref in blocks:
         d = o.decode_block(ref, longflag=blk.longflag)
         assert np.array_equal(d.seqlen, blk.seqlen)
         assert d.seq.tobytes() == blk.seq.tobytes()
         assert d.qual.tobytes() == blk.qual.tobytes()
-        assert d.ids.tobytes() == blk.ids.tobytes()
-        assert np.array_equal(d.idlen, blk.idlen)
+        if kw["id_rule"]:
+            # rule-based IDs (IDProcess::decodeIDS) are host string logic: regenerated and checked against the
+            # original IDs in tests/test_host_layer.py; the oracle leaves the ID buffer empty
+            assert d.ids.shape[0] == 0
+        else:
+            assert d.ids.tobytes() == blk.ids.tobytes()
+            assert np.array_equal(d.idlen, blk.idlen)
 
 
 def test_md5_known_answers():
