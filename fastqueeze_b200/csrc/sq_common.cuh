@@ -80,39 +80,6 @@ SQ_HD u32 seq_val(u32 c) {
         default: return 4;
     }
 }
-// only letters map; '!'|0x20 etc. must not alias: restrict to alphabetic input
-SQ_HD u32 seq_val_exact(u32 c) {
-    u32 l = c | 0x20;
-    if (l < 'a' || l > 'z' || (c & 0x80)) return 4;
-    if ((c & ~0x20u) < 'A' || (c & ~0x20u) > 'Z') return 4;
-    return seq_val(c);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Division of a 32-bit numerator by an invariant divisor 2 <= d <= 65535 (range / tot in
-// RangeCoder::Encode, e.g. @0x422010).  Granlund-Montgomery round-up method, exact for every
-// 32-bit n:  l = ceil(log2 d), m = floor(2^32 (2^l - d) / d) + 1,
-//            t = mulhi(m, n), q = (t + ((n - t) >> 1)) >> (l - 1).
-struct FastDiv { u32 m; u32 sh; };
-SQ_HD FastDiv fastdiv_make(u32 d) {
-    u32 l = 0;
-    while ((1u << l) < d) l++;
-    FastDiv f;
-    f.m = (u32)((((u64)1 << 32) * (((u64)1 << l) - d)) / d) + 1;
-    f.sh = l - 1;
-    return f;
-}
-SQ_HD u32 mulhi32(u32 a, u32 b) {
-#ifdef __CUDA_ARCH__
-    return __umulhi(a, b);
-#else
-    return (u32)(((u64)a * b) >> 32);
-#endif
-}
-SQ_HD u32 fastdiv_do(u32 n, FastDiv f) {
-    u32 t = mulhi32(f.m, n);
-    return (t + ((n - t) >> 1)) >> f.sh;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Serial range coder (RangeCoder, inlined in the reference: encode @0x422010-0x422085, flush

@@ -1,3 +1,4 @@
+# A/B helper: decode timing for several values of SQ_DEC_CARVEOUT ("auto" = computed from the co-resident CTAs)
 # usage: quick_env.sh <blocks> <carve values...>
 b=$1; shift
 for c in "$@"; do

@@ -1,3 +1,4 @@
+# A/B helper: time the decode of N blocks (default 1) with each library variant under _variants/ (gpurun_out is not shipped)
 # time the decode of 1 block with each library variant under _variants/
 for v in _variants/*.so; do
   cp $v fastqueeze_b200/libseqarc_b200.so
