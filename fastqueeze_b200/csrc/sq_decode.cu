@@ -440,6 +440,9 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &la
     return b;
 }
 
+// base code -> letter without a table in local memory
+SQ_D u32 base_char(u32 b) { return (0x54474341u >> (8 * b)) & 0xffu; }      // "ACGT"
+
 // small side streams: "u32le count | range-coder bytes" with a fresh local model (lane 0 only)
 template <int N>
 SQ_D u32 dec_small(const DecBlock &d, int tag, SmModel<N> &m, u8 *arr, u32 cap, int mode) {
@@ -494,7 +497,6 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm.rlut[i] = recip_est(i < 2 ? 2 : i);
     __syncthreads();
     if (d.status != 0) return;
-    const char tbl[] = "ACGT";
 #ifdef SQ_DEBUG_TIMING
     long long t_begin = clock64();
 #define SQ_TICK(name) if (blockIdx.x == 0 && lane == 0) printf("dec warp %d %s: %lld cycles\n", wid, name, clock64() - t_begin)
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
             if (!flagged) {
                 for (int i = 0; i < len; i++) {
                     u32 bb = decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol);
-                    if (lane == 0) seq[i] = (u8)tbl[bb];
+                    if (lane == 0) seq[i] = base_char(bb);
                 }
                 continue;
             }
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
                 for (int i = 0; i < len; i++) {
                     u32 c;
                     if (mq >= (int)(int8_t)__ldcg(qual + i)) { c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
-                    else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol)];
+                    else c = base_char(decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol));
                     if (lane == 0) seq[i] = (u8)c;
                 }
                 continue;
@@ -641,10 +643,10 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
                     if (run == gap) {                          // @0x429b40
                         gap = 0xffffffffu;
                         if (remaining) { remaining--; gap = i_pos < n_pos ? __ldcg(d_pos + i_pos) : 0; i_pos++; }
-                        c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol)];
+                        c = base_char(decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol));
                         run = 0;
                     } else { run++; c = i_ch < n_ch ? __ldcg(d_ch + i_ch) : 'N'; i_ch++; }
-                } else c = (u8)tbl[decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol)];
+                } else c = base_char(decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol));
                 if (lane == 0) seq[i] = (u8)c;
             }
         }
