@@ -11,16 +11,30 @@ namespace sqhost {
 
 bool InFile::open(const std::string &path) {
     close();
-    gzFile g = gzopen(path.c_str(), "rb");
-    if (g) gzbuffer(g, 1 << 20);
-    f_ = g;
-    return f_ != nullptr;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    unsigned char magic[2] = {0, 0};
+    size_t k = fread(magic, 1, 2, f);
+    if (k == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {       // gzip member
+        fclose(f);
+        gzFile g = gzopen(path.c_str(), "rb");
+        if (g) gzbuffer(g, 1 << 20);
+        f_ = g;
+        return f_ != nullptr;
+    }
+    rewind(f);
+    setvbuf(f, nullptr, _IOFBF, 1 << 20);
+    plain_ = f;
+    return true;
 }
 void InFile::close() {
     if (f_) gzclose((gzFile)f_);
+    if (plain_) fclose(plain_);
     f_ = nullptr;
+    plain_ = nullptr;
 }
 size_t InFile::read(void *dst, size_t n) {
+    if (plain_) return fread(dst, 1, n, plain_);
     size_t got = 0;
     while (got < n) {
         unsigned chunk = (unsigned)std::min<size_t>(n - got, 1u << 30);
@@ -33,7 +47,7 @@ size_t InFile::read(void *dst, size_t n) {
 bool InFile::getline(std::vector<char> &out) {
     char buf[1 << 16];
     bool any = false;
-    while (gzgets((gzFile)f_, buf, sizeof buf)) {
+    while (plain_ ? fgets(buf, sizeof buf, plain_) != nullptr : gzgets((gzFile)f_, buf, sizeof buf) != nullptr) {
         size_t n = strlen(buf);
         out.insert(out.end(), buf, buf + n);
         any = true;
@@ -172,13 +186,21 @@ void parse_block(const std::vector<char> &t1, const std::vector<char> &t2, bool 
     }
 }
 
+bool BlockReader::next_raw(Raw &r) {
+    if (!next_text(r.t1, r.t2)) return false;
+    r.src_off[0] = off_[0]; r.src_off[1] = off_[1];
+    off_[0] += r.t1.size(); off_[1] += r.t2.size();
+    return true;
+}
+void BlockReader::parse_raw(const Raw &r, bool pe, MemBuf &mb) {
+    mb.src_off[0] = r.src_off[0]; mb.src_off[1] = r.src_off[1];
+    mb.src_bytes[0] = r.t1.size(); mb.src_bytes[1] = r.t2.size();
+    parse_block(r.t1, r.t2, pe, mb);
+}
 bool BlockReader::next(MemBuf &mb) {
-    std::vector<char> t1, t2;
-    if (!next_text(t1, t2)) return false;
-    mb.src_off[0] = off_[0]; mb.src_off[1] = off_[1];
-    mb.src_bytes[0] = t1.size(); mb.src_bytes[1] = t2.size();
-    off_[0] += t1.size(); off_[1] += t2.size();
-    parse_block(t1, t2, pe_, mb);
+    Raw r;
+    if (!next_raw(r)) return false;
+    parse_raw(r, pe_, mb);
     return true;
 }
 

@@ -39,13 +39,14 @@ public:
     ~InFile() { close(); }
     bool open(const std::string &path);
     void close();
-    bool ok() const { return f_ != nullptr; }
+    bool ok() const { return f_ != nullptr || plain_ != nullptr; }
     size_t read(void *dst, size_t n);                 // like fread(dst, 1, n)
     bool getline(std::vector<char> &append_to);       // appends one line including its '\n'; false at end of input
     static bool is_gz_name(const std::string &path) { return path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0; }
 
 private:
-    void *f_ = nullptr;                               // gzFile
+    void *f_ = nullptr;                               // gzFile (gzip input)
+    FILE *plain_ = nullptr;                           // plain input: read directly, no pass through zlib's buffer
 };
 
 class BlockReader {
@@ -59,6 +60,11 @@ public:
     bool next_text(std::vector<char> &t1, std::vector<char> &t2);
     // next block parsed into a MemBuf; false at end of input; throws std::runtime_error on malformed FASTQ
     bool next(MemBuf &mb);
+    // the same in two steps, so that callers can parse several blocks in parallel: next_raw cuts the text
+    // (sequential), parse_raw fills the MemBuf (independent per block)
+    struct Raw { std::vector<char> t1, t2; uint64_t src_off[2] = {0, 0}; };
+    bool next_raw(Raw &r);
+    static void parse_raw(const Raw &r, bool pe, MemBuf &mb);
     static int get_end_pos(int len, const char *buf, int valid, const std::string &firstline);
 
 private:

@@ -7,7 +7,12 @@
 // like the reference does (parseOptFromFile @0x4062e0) because none of the three is stored in the .arc.
 #include <sys/stat.h>
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <future>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -169,19 +174,47 @@ static int do_compress(const Opt &o) {
     if (!rd.ok()) die("cannot open input");
     ArcWriter wr;
     if (!wr.open(arcname)) die("cannot create " + arcname);
-    int batch = o.batch > 0 ? o.batch : 64;
+    int batch = o.batch > 0 ? o.batch : 128;      // blocks per GPU call: the chain kernels want as many blocks per wave as the workspace holds
     std::vector<MemBuf> mbs;
     std::vector<std::vector<uint8_t>> recs;
     uint64_t nblocks = 0, in_bytes = 0;
     auto t0 = std::chrono::steady_clock::now();
-    for (bool more = true; more;) {
-        mbs.clear();
-        while ((int)mbs.size() < batch) {
-            mbs.emplace_back();
-            if (!rd.next(mbs.back())) { mbs.pop_back(); more = false; break; }
-            if (mbs.back().comment != ap.comment) die("'+' lines must be all bare or all a copy of the ID");
+    // Host pipeline: the reader cuts block texts sequentially (cheap), a pool parses them into MemBufs in parallel,
+    // and the next batch is cut + parsed while the GPU encodes the current one.
+    const bool rd_pe = pe;
+    auto load_batch = [&rd, batch, rd_pe]() {
+        std::vector<BlockReader::Raw> raws;
+        while ((int)raws.size() < batch) {
+            raws.emplace_back();
+            if (!rd.next_raw(raws.back())) { raws.pop_back(); break; }
         }
+        std::vector<MemBuf> out(raws.size());
+        std::string err;
+        std::mutex mu;
+        std::atomic<size_t> next{0};
+        unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)raws.size()}));
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++)
+            pool.emplace_back([&]() {
+                for (size_t i; (i = next.fetch_add(1)) < raws.size();) {
+                    try { BlockReader::parse_raw(raws[i], rd_pe, out[i]); }
+                    catch (const std::exception &e) { std::lock_guard<std::mutex> g(mu); if (err.empty()) err = e.what(); }
+                    std::vector<char>().swap(raws[i].t1);
+                    std::vector<char>().swap(raws[i].t2);
+                }
+            });
+        for (auto &th : pool) th.join();
+        if (!err.empty()) throw std::runtime_error(err);
+        return out;
+    };
+    std::future<std::vector<MemBuf>> ahead = std::async(std::launch::async, load_batch);
+    for (;;) {
+        mbs = ahead.get();
         if (mbs.empty()) break;
+        bool full = (int)mbs.size() == batch;
+        if (full) ahead = std::async(std::launch::async, load_batch);      // overlaps the GPU work below
+        for (auto &m : mbs)
+            if (m.comment != ap.comment) die("'+' lines must be all bare or all a copy of the ID");
         int n = (int)mbs.size();
         std::vector<sq_block_in> in(n);
         std::vector<sq_block_out> out(n);
@@ -198,6 +231,7 @@ static int do_compress(const Opt &o) {
             in_bytes += mbs[i].src_bytes[0] + mbs[i].src_bytes[1];
         }
         nblocks += n;
+        if (!full) break;
     }
     if (!wr.finish(ap)) die("write failed");
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -250,7 +284,7 @@ static int do_decompress(const Opt &o) {
     if (ar.p.usemodel && sq_load_model(c, ar.p.model.data(), ar.p.model.size()) != SQ_OK) die(sq_last_error(c));
     FILE *f1 = fopen(n1.c_str(), "wb"), *f2 = pe ? fopen(n2.c_str(), "wb") : nullptr;
     if (!f1 || (pe && !f2)) die("cannot create output");
-    int batch = o.batch > 0 ? o.batch : 64;
+    int batch = o.batch > 0 ? o.batch : 128;      // blocks per GPU call: the chain kernels want as many blocks per wave as the workspace holds
     std::string o1, o2;
     for (size_t b0 = 0; b0 < ar.idx.size(); b0 += batch) {
         int n = (int)std::min<size_t>(batch, ar.idx.size() - b0);
@@ -275,25 +309,43 @@ static int do_decompress(const Opt &o) {
             const char *w = rc == SQ_ERR_MD5_NAME ? "Name md5 unequal" : rc == SQ_ERR_MD5_SEQ ? "Seq md5 unequal" : rc == SQ_ERR_MD5_QUAL ? "Qual md5 unequal" : sq_last_error(c);
             die(std::string("decode: ") + w);
         }
-        for (int i = 0; i < n; i++) {
-            MemBuf &m = mbs[i];
-            m.idlen.resize(dec[i].nreads); m.seqlen.resize(dec[i].nreads);
-            if (rule) {               // IDProcess::decodeIDS @0x430610: regenerate the IDs from the block's first ID
-                const uint8_t *pay = nullptr, *md5 = nullptr;
-                size_t plen = 0;
-                if (!find_id_payload(recs[i], lens[i], ar.p.md5, &pay, &plen, &md5)) die("decode: block without an ID stream");
-                m.ids.clear(); m.idlen.clear();
-                if (!decode_ids(pay, plen, ar.p.idbin, m.seqlen.data(), dec[i].nreads, m.ids, m.idlen)) die("decode: bad rule-based ID record");
-                if (md5) {
-                    uint8_t dig[16];
-                    md5_digest(m.ids.data(), m.ids.size(), dig);
-                    if (memcmp(dig, md5, 16) != 0) die("decode: Name md5 unequal");
+        // regenerate rule-based IDs and render the FASTQ text of the batch's blocks in parallel, then write in order
+        std::vector<std::string> t1(n), t2(n);
+        std::string err;
+        std::mutex mu;
+        std::atomic<int> next{0};
+        auto work = [&]() {
+            for (int i; (i = next.fetch_add(1)) < n;) {
+                MemBuf &m = mbs[i];
+                m.idlen.resize(dec[i].nreads); m.seqlen.resize(dec[i].nreads);
+                const char *bad = nullptr;
+                if (rule) {               // IDProcess::decodeIDS @0x430610: regenerate the IDs from the block's first ID
+                    const uint8_t *pay = nullptr, *md5 = nullptr;
+                    size_t plen = 0;
+                    if (!find_id_payload(recs[i], lens[i], ar.p.md5, &pay, &plen, &md5)) bad = "decode: block without an ID stream";
+                    else {
+                        m.ids.clear(); m.idlen.clear();
+                        if (!decode_ids(pay, plen, ar.p.idbin, m.seqlen.data(), dec[i].nreads, m.ids, m.idlen)) bad = "decode: bad rule-based ID record";
+                        else if (md5) {
+                            uint8_t dig[16];
+                            md5_digest(m.ids.data(), m.ids.size(), dig);
+                            if (memcmp(dig, md5, 16) != 0) bad = "decode: Name md5 unequal";
+                        }
+                    }
                 }
+                if (bad) { std::lock_guard<std::mutex> g(mu); if (err.empty()) err = bad; continue; }
+                m.comment = ar.p.comment;
+                render_block(m, pe, t1[i], t2[i]);
             }
-            m.comment = ar.p.comment;
-            render_block(m, pe, o1, o2);
-            fwrite(o1.data(), 1, o1.size(), f1);
-            if (pe) fwrite(o2.data(), 1, o2.size(), f2);
+        };
+        unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)n}));
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
+        for (auto &th : pool) th.join();
+        if (!err.empty()) die(err);
+        for (int i = 0; i < n; i++) {
+            fwrite(t1[i].data(), 1, t1[i].size(), f1);
+            if (pe) fwrite(t2[i].data(), 1, t2[i].size(), f2);
         }
     }
     fclose(f1);

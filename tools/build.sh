@@ -18,7 +18,7 @@ $NVCC -shared -o $OUT build/sq_encode.o build/sq_decode.o build/sq_api.o
 echo "built $OUT"
 # host driver (C++): FASTQ block cutter, .arc packer, CLI -> fastqueeze_b200/seqarc_b200
 g++ -O2 -std=c++17 -Wall -o fastqueeze_b200/seqarc_b200 host/seqarc_b200_main.cpp host/fastq_block.cpp host/arc_file.cpp host/id_process.cpp \
-    -Lfastqueeze_b200 -lseqarc_b200 -lz -Wl,-rpath,'$ORIGIN'
+    -Lfastqueeze_b200 -lseqarc_b200 -lz -pthread -Wl,-rpath,'$ORIGIN'
 echo "built fastqueeze_b200/seqarc_b200"
 g++ -O2 -std=c++17 -Wall -shared -fPIC -o fastqueeze_b200/libseqarc_host.so host/host_capi.cpp host/fastq_block.cpp host/arc_file.cpp host/id_process.cpp -lz
 echo "built fastqueeze_b200/libseqarc_host.so"
