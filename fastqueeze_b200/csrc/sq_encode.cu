@@ -770,36 +770,84 @@ __global__ void __launch_bounds__(32) k_md5(const BlockDesc *bd, BlockState *bs,
 // block's concatenated quality bytes, end of data = byte count.  Serial per
 // block; doubles exactly as the reference (IEEE sqrt / div, round half up).
 SQ_D double rnd_half_up(double x) { return floor(x + 0.5); }
+
+// One warp per block.  The doubles only ever see pairs of byte values, so the warp first tabulates, with the
+// reference's own arithmetic, g(lo, hi) = round(sqrt(lo * hi)) and ok(lo, hi) = (r > g / lo && r > hi / g) for
+// every pair below 128 (the "extend upwards" test uses (min, c), the "extend downwards" test (c, max): the same
+// function of the ordered pair).  The scan itself is serial -- every run starts where the previous one closed --
+// and runs on lane 0 over 4-KiB tiles staged in shared memory by the whole warp; a run is filled in the tile
+// when it closes, the part of it that lies in earlier tiles by all lanes in global memory.
+#define RB_TILE 4096
+struct RbSmem {
+    u8 g[128 * 128];             // fill value of the ordered pair (lo, hi)
+    u32 ok[128 * 128 / 32];      // bit (lo * 128 + hi)
+    u32 tile[RB_TILE / 4];
+    u64 patch_start;
+    u32 patch_v;
+};
 __global__ void __launch_bounds__(32) k_rblock(const BlockDesc *bd, int B, double r) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ RbSmem sm;
+    int b = blockIdx.x, lane = threadIdx.x;
     if (b >= B) return;
     u8 *q = bd[b].qual_work;
-    u64 n = bd[b].seqbytes;
+    const u64 n = bd[b].seqbytes;
     if (n == 0) return;
-    u64 start = 0, i = 1;
-    int mn = q[0], mx = q[0];
-    for (;;) {
-        bool close = false;
-        int ch = 0;
-        if (i >= n) close = true;
-        else {
-            ch = q[i];
-            if (ch >= mn && ch <= mx) { i++; continue; }
-            if (ch > mx) {
-                double g = rnd_half_up(sqrt((double)ch * mn));
-                if (r > g / mn && r > ch / g) { mx = ch; i++; continue; }
-            } else {
-                double g = rnd_half_up(sqrt((double)ch * mx));
-                if (r > g / ch && r > mx / g) { mn = ch; i++; continue; }
+    for (int w = lane; w < 128 * 128 / 32; w += 32) {
+        u32 bits = 0;
+        for (int k = 0; k < 32; k++) {
+            int idx = w * 32 + k, lo = idx >> 7, hi = idx & 127;
+            u8 gv = 0;
+            if (lo > 0 && hi >= lo) {
+                double g = rnd_half_up(sqrt((double)hi * lo));
+                gv = (u8)g;
+                if (r > g / lo && r > hi / g) bits |= 1u << k;
             }
-            close = true;
+            sm.g[idx] = gv;
         }
-        if (close) {
-            u8 v = (u8)rnd_half_up(sqrt((double)mn * mx));
-            for (u64 k = start; k < i; k++) q[k] = v;
-            if (i >= n) return;
-            start = i; mn = mx = ch; i++;
+        sm.ok[w] = bits;
+    }
+    __syncwarp();
+    u8 *tb = (u8 *)sm.tile;
+    // scan state (lane 0): the open run [start, i) with its min / max
+    u64 start = 0;
+    int mn = 0, mx = 0;
+    bool open = false;
+    for (u64 t0 = 0; t0 < n; t0 += RB_TILE) {
+        u32 tn = (u32)(n - t0 < RB_TILE ? n - t0 : RB_TILE);
+        for (u32 k = lane; k < tn; k += 32) tb[k] = q[t0 + k];
+        __syncwarp();
+        if (lane == 0) {
+            sm.patch_start = ~0ull;
+            for (u32 k = 0; k < tn; k++) {
+                int ch = tb[k] & 127;
+                if (!open) { open = true; start = t0 + k; mn = mx = ch; continue; }
+                if (ch >= mn && ch <= mx) continue;
+                if (ch > mx) { int idx = mn * 128 + ch; if ((sm.ok[idx >> 5] >> (idx & 31)) & 1) { mx = ch; continue; } }
+                else { int idx = ch * 128 + mx; if ((sm.ok[idx >> 5] >> (idx & 31)) & 1) { mn = ch; continue; } }
+                // close [start, t0 + k): the part inside this tile now, an earlier part as a patch
+                u8 v = sm.g[mn * 128 + mx];
+                u32 from = start >= t0 ? (u32)(start - t0) : 0;
+                for (u32 j = from; j < k; j++) tb[j] = v;
+                if (start < t0) { sm.patch_start = start; sm.patch_v = v; }
+                start = t0 + k; mn = mx = ch;
+            }
+            if (t0 + tn >= n && open) {                      // end of data closes the last run
+                u8 v = sm.g[mn * 128 + mx];
+                u32 from = start >= t0 ? (u32)(start - t0) : 0;
+                for (u32 j = from; j < tn; j++) tb[j] = v;
+                if (start < t0) { sm.patch_start = start; sm.patch_v = v; }
+                start = n;
+            }
         }
+        __syncwarp();
+        // at most one run reaches into a tile from the left, so one patch per tile
+        u64 ps = sm.patch_start;
+        if (ps != ~0ull) { u8 v = (u8)sm.patch_v; for (u64 j = ps + lane; j < t0; j += 32) q[j] = v; }
+        // write back what is final: everything before the run that is still open
+        u64 os = __shfl_sync(0xffffffffu, start, 0);
+        u32 fin = os >= t0 + tn ? tn : (os > t0 ? (u32)(os - t0) : 0);
+        for (u32 k = lane; k < fin; k += 32) q[t0 + k] = tb[k];
+        __syncwarp();
     }
 }
 
@@ -1121,7 +1169,7 @@ cudaError_t sqk_prep(const EncWave &w, cudaStream_t st, u64 *launches) {
 }
 
 cudaError_t sqk_rblock(const EncWave &w, double r, cudaStream_t st, u64 *launches) {
-    k_rblock<<<cdiv(w.B, 32), 32, 0, st>>>(w.bd, w.B, r);
+    k_rblock<<<w.B, 32, 0, st>>>(w.bd, w.B, r);
     *launches += 1;
     return cudaGetLastError();
 }

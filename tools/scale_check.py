@@ -43,6 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=24)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
+    ap.add_argument("--lossy", type=float, default=0.0, help="R-Block ratio (-l); the reference then runs under the newline-guard shim")
     a = ap.parse_args()
     import torch
     dev = torch.device("cuda:0")
@@ -56,15 +57,24 @@ def main():
                 bench.fastq_text(blk, 1).tofile(y)
         nbytes = os.path.getsize(f1) + os.path.getsize(f2)
         res = {"blocks": a.blocks, "fastq_bytes": nbytes, "fastq_md5": [md5(f1), md5(f2)]}
+        lossy = ["-l", "%g" % a.lossy] if a.lossy else []
+        res["lossy"] = a.lossy
         t0 = time.perf_counter()
-        rc, log = po.run_ref(["-c", "-t", "1", "-f", "-1", f1, "-2", f2, "-o", "ref"], tmp)
+        rc, log = po.run_ref(["-c", "-t", "1", "-f"] + lossy + ["-1", f1, "-2", f2, "-o", "ref"], tmp, lossy_shim=bool(lossy))
         assert rc == 0, log[-1500:]
         res["ref_c_t1_s"] = round(time.perf_counter() - t0, 1)
-        res["ours_c_s"] = round(run([CLI, "-c", "-f", "-1", f1, "-2", f2, "-o", "ours"], tmp), 1)
+        res["ours_c_s"] = round(run([CLI, "-c", "-f"] + lossy + ["-1", f1, "-2", f2, "-o", "ours"], tmp), 1)
         res["arc_bytes"] = os.path.getsize(os.path.join(tmp, "ref.arc"))
         res["arc_md5_ref"], res["arc_md5_ours"] = md5(os.path.join(tmp, "ref.arc")), md5(os.path.join(tmp, "ours.arc"))
         res["archive_identical"] = res["arc_md5_ref"] == res["arc_md5_ours"]
         res["ours_d_s"] = round(run([CLI, "-d", "-f", "ref.arc", "-o", "back"], tmp), 1)
+        if lossy:       # lossy: the decoded qualities are the smoothed ones -- compare with the reference's own decode
+            rc, log = po.run_ref(["-d", "-t", str(a.threads), "-f", "ref.arc", "-o", "rback"], tmp)
+            assert rc == 0, log[-1500:]
+            res["decode_equals_reference_decode"] = [md5(os.path.join(tmp, "back_%d.fastq" % k)) for k in (1, 2)] == \
+                                                    [md5(os.path.join(tmp, "rback_%d.fastq" % k)) for k in (1, 2)]
+            print(json.dumps(res))
+            return
         res["decode_of_ref_archive_ok"] = [md5(os.path.join(tmp, "back_1.fastq")), md5(os.path.join(tmp, "back_2.fastq"))] == res["fastq_md5"]
         rc, log = po.run_ref(["-c", "-t", str(a.threads), "-f", "-1", f1, "-2", f2, "-o", "mt"], tmp)
         assert rc == 0, log[-1500:]
