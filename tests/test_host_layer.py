@@ -184,3 +184,22 @@ def test_id_bin_analysis_on_other_id_styles(hl):
     assert run([b"r.%d" % (2 * i) for i in range(1, 50)])[0] == 0                # step 2 is not a rule
     r, b = run([b"r.%d len=50" % i for i in range(1, 50)])
     assert r == 1 and b[:6] == bytes([1, 0, 0, 1, 0, 3])                         # "len" token + read length
+
+
+def test_mixed_plus_lines_are_refused(hl):
+    """The archive only records WHETHER the '+' lines repeat the ID; a mix breaks the reference's own round trip
+    (measured) and is an input error here."""
+    from tools.make_golden import plus_lines
+    t = common.case_fastq("se100_q8")[0]
+    lines = plus_lines(t).split(b"\n")
+    lines[6] = b"+"                      # second record back to a bare '+'
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "mixed.fq")
+        open(p, "wb").write(b"\n".join(lines))
+        cap = 8
+        nr, s1, s2 = np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        assert hl.sqh_cut_blocks(p.encode(), None, 50 << 20, nr.ctypes.data, s1.ctypes.data, s2.ctypes.data, cap) == -2
+        q = os.path.join(d, "ok.fq")
+        open(q, "wb").write(plus_lines(t))
+        assert hl.sqh_cut_blocks(q.encode(), None, 50 << 20, nr.ctypes.data, s1.ctypes.data, s2.ctypes.data, cap) == 1
+        assert int(nr[0]) == 4000 and int(s1[0]) == len(plus_lines(t))
