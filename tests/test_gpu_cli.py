@@ -23,7 +23,9 @@ IDENTICAL = ["err_pe1000", "err_pe1000_nomd5", "srr_pe100", "illumina_pe150", "i
              # "+<ID>" separator lines
              "se100_q8_plus", "illumina_pe150_plus_3blocks",
              # reads longer than 65,535 bases (compressLen_long, long flag in the block index)
-             "long_se"]
+             "long_se",
+             # more ID styles (BGI, pre-1.8 Illumina, SRA dump with a length field)
+             "bgi_pe100", "old_illumina_pe100", "sra_len_se100"]
 
 
 def _setup(name, d):

@@ -59,6 +59,10 @@ CASES = [
          config={"BlockSize(M)": 1}, plus=True),
     # reads longer than 65,535 bases: compressLen_long @0x423710 and the long flag in the block index
     dict(name="long_se", src=dict(kind="long_se", n_templates=4, seed=9), pe=False, opts=[], config=None),
+    # more ID styles for the ID-bin analysis / name model (BGI, pre-1.8 Illumina, SRA dump with a length field)
+    dict(name="bgi_pe100", src=dict(kind="bgi_pe100", n_templates=1200, seed=13), pe=True, opts=[], config=None),
+    dict(name="old_illumina_pe100", src=dict(kind="old_illumina_pe100", n_templates=1200, seed=14), pe=True, opts=[], config=None),
+    dict(name="sra_len_se100", src=dict(kind="sra_len_se100", n_templates=2500, seed=15), pe=False, opts=[], config=None),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]

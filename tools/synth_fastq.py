@@ -50,6 +50,38 @@ def srr_ids(n_templates, first=0, mate=None):
     return ids
 
 
+def bgi_ids(n_templates, first=0, mate=None):
+    """'V300012345L1C001R0010000001/1' -- BGI / MGI style: lane, column, row, running number, mate suffix."""
+    ids = []
+    for i in range(first, first + n_templates):
+        s = b"V300012345L1C%03dR%03d%07d" % (1 + (i // 9000) % 8, 1 + (i // 300) % 30, i % 300 * 13 + 1)
+        if mate is not None:
+            s += b"/%d" % mate
+        ids.append(s)
+    return ids
+
+
+def old_illumina_ids(n_templates, rng, first=0, mate=None):
+    """'HWUSI-EAS100R:6:73:941:1973#0/1' -- pre-CASAVA-1.8 style, coordinates not zero padded (variable width)."""
+    x = rng.integers(1, 20000, n_templates)
+    y = rng.integers(1, 20000, n_templates)
+    ids = []
+    for i in range(n_templates):
+        s = b"HWUSI-EAS100R:6:%d:%d:%d#0" % (1 + ((first + i) // 2000) % 120, x[i], y[i])
+        if mate is not None:
+            s += b"/%d" % mate
+        ids.append(s)
+    return ids
+
+
+def sra_len_ids(n_templates, rng, first=0):
+    """'SRR001666.1 071112_SLXA-EAS1_s_7:5:1:817:345 length=100' -- SRA dump with the original name and a length field."""
+    x = rng.integers(1, 2000, n_templates)
+    y = rng.integers(1, 2000, n_templates)
+    return [b"SRR001666.%d 071112_SLXA-EAS1_s_7:5:%d:%d:%d length=100" % (first + i + 1, 1 + ((first + i) // 500) % 300, x[i], y[i])
+            for i in range(n_templates)]
+
+
 def make_block(kind="illumina_pe150", n_templates=1000, seed=7, first=0, n_rate=0.0, hash_tail=0.0):
     """Return dict(ids, idlen, seq, qual, seqlen) numpy arrays of one block.
 
@@ -67,13 +99,24 @@ def make_block(kind="illumina_pe150", n_templates=1000, seed=7, first=0, n_rate=
         return dict(ids=np.frombuffer(b"".join(idl), dtype=np.uint8).copy(), idlen=np.array([len(x) for x in idl], np.uint16),
                     seq=BASES[rng.integers(0, 4, tot)], qual=(np.clip(np.rint(rng.normal(20, 6, tot)), 2, 40).astype(np.uint8) + 33),
                     seqlen=np.array(lens, np.int32), pe=False)
-    pe = kind != "se100_q8"
+    pe = kind not in ("se100_q8", "sra_len_se100")
     L = 150 if kind == "illumina_pe150" else 100
     n = n_templates * (2 if pe else 1)
-    if kind == "srr_pe100":
-        a, b = srr_ids(n_templates, first, 1), srr_ids(n_templates, first, 2)
-        idl = [None] * n
-        idl[0::2], idl[1::2] = a, b
+    if kind in ("srr_pe100", "bgi_pe100", "old_illumina_pe100", "sra_len_se100"):
+        if kind == "srr_pe100":
+            a, b = srr_ids(n_templates, first, 1), srr_ids(n_templates, first, 2)
+        elif kind == "bgi_pe100":
+            a, b = bgi_ids(n_templates, first, 1), bgi_ids(n_templates, first, 2)
+        elif kind == "old_illumina_pe100":
+            a = old_illumina_ids(n_templates, np.random.default_rng(seed + 1000003), first, 1)
+            b = old_illumina_ids(n_templates, np.random.default_rng(seed + 1000003), first, 2)
+        else:
+            a, b = sra_len_ids(n_templates, np.random.default_rng(seed + 1000003), first), None
+        if pe:
+            idl = [None] * n
+            idl[0::2], idl[1::2] = a, b
+        else:
+            idl = a
         ids = np.frombuffer(b"".join(idl), dtype=np.uint8).copy()
         idlen = np.array([len(s) for s in idl], dtype=np.uint16)
     else:
