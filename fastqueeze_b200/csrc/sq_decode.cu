@@ -484,16 +484,104 @@ struct MainSmem {
     u32 cnts[5];               // n_tip, n_ch, n_mq, n_cnt, n_pos (published by lane 0 of the seq warp)
     int side_err;
     volatile u32 qprog;        // reads whose qualities are complete
+    volatile u32 sprog;        // reads whose bases are complete (only read by the in-kernel MD5 chaser)
 };
 
+// ---------------------------------------------------------------------------------------------
+// blockMd5Verify @0x414e00 inside the decode kernel: the names warp is done after ~10 % of the kernel's time;
+// its lane 0 then digests the ID buffer and CHASES the quality and base warps, hashing their output 64 bytes at a
+// time as whole reads are published (qprog / sprog), so that the digests are ready when the last read is.
+struct Md5Run {
+    u32 h[4];
+    u64 pos;                     // bytes digested (multiple of 64 until the end)
+    SQ_D void init() { h[0] = 0x67452301u; h[1] = 0xefcdab89u; h[2] = 0x98badcfeu; h[3] = 0x10325476u; pos = 0; }
+    // digest whole chunks of p[pos, avail), at most `maxchunks`; returns true if it did any work
+    SQ_D bool feed(const u8 *p, u64 avail, int maxchunks) {
+        bool any = false;
+        u32 w[16];
+        const bool al = (((uintptr_t)p) & 15) == 0;
+        while (pos + 64 <= avail && maxchunks-- > 0) {
+            if (al) {
+                const uint4 *p4 = (const uint4 *)(p + pos);
+                uint4 x0 = __ldcg(p4), x1 = __ldcg(p4 + 1), x2 = __ldcg(p4 + 2), x3 = __ldcg(p4 + 3);
+                w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
+                w[8] = x2.x; w[9] = x2.y; w[10] = x2.z; w[11] = x2.w; w[12] = x3.x; w[13] = x3.y; w[14] = x3.z; w[15] = x3.w;
+            } else {
+                for (int k = 0; k < 16; k++) {
+                    const u8 *b = p + pos + 4 * k;
+                    w[k] = (u32)__ldcg(b) | ((u32)__ldcg(b + 1) << 8) | ((u32)__ldcg(b + 2) << 16) | ((u32)__ldcg(b + 3) << 24);
+                }
+            }
+            md5_chunk(h, w);
+            pos += 64;
+            any = true;
+        }
+        return any;
+    }
+    // the last (< 64) bytes + padding; `total` = length of the whole buffer
+    SQ_D void finish(const u8 *p, u64 total, u8 out[16]) {
+        u8 tail[128];
+        u32 rem = (u32)(total - pos);
+        for (int k = 0; k < 128; k++) tail[k] = 0;
+        for (u32 k = 0; k < rem; k++) tail[k] = __ldcg(p + pos + k);
+        tail[rem] = 0x80;
+        u32 tl = rem < 56 ? 64 : 128;
+        u64 bits = total * 8;
+        for (int k = 0; k < 8; k++) tail[tl - 8 + k] = (u8)(bits >> (8 * k));
+        u32 w[16];
+        for (u32 o = 0; o < tl; o += 64) {
+            for (int k = 0; k < 16; k++) w[k] = get_u32le(tail + o + 4 * k);
+            md5_chunk(h, w);
+        }
+        for (int k = 0; k < 4; k++) put_u32le(out + 4 * k, h[k]);
+    }
+};
+SQ_D bool md5_equal(const u8 *a, const u8 *b) {
+    bool ok = true;
+    for (int k = 0; k < 16; k++) ok = ok && (a[k] == b[k]);
+    return ok;
+}
+// lane 0 of the names warp, after the names are done.  Never waits on a warp that has given up: a block whose
+// status turned non-zero is left alone.
+SQ_D void md5_chase(DecBlock &d, volatile u32 *qprog, volatile u32 *sprog, const u32 *seqoff, u32 nreads, int id_rule) {
+    volatile i32 *status = (volatile i32 *)&d.status;
+    u8 dig[16];
+    if (!id_rule && d.has_md5[0]) {
+        md5_buffer(d.ids, d.idbytes, dig);
+        if (!md5_equal(dig, d.md5[0]) && *status == 0) *status = -8;          // SQ_ERR_MD5_NAME
+    }
+    if (!d.has_md5[1] && !d.has_md5[2]) return;
+    const u64 total = d.seqbytes;
+    Md5Run rs, rq;
+    rs.init(); rq.init();
+    bool want_s = d.has_md5[1] != 0, want_q = d.has_md5[2] != 0;
+    u64 as = 0, aq = 0;                               // bytes of reads published so far
+    for (;;) {
+        bool done_s = !want_s || (as == total && rs.pos + 64 > total);
+        bool done_q = !want_q || (aq == total && rq.pos + 64 > total);
+        if (done_s && done_q) break;
+        if (*status != 0) return;
+        u32 ps = *sprog, pq = *qprog;
+        __threadfence_block();
+        as = seqoff[ps < nreads ? ps : nreads];
+        aq = seqoff[pq < nreads ? pq : nreads];
+        bool any = false;
+        if (want_s) any |= rs.feed(d.seq, as, 64);
+        if (want_q) any |= rq.feed(d.qual, aq, 64);
+        if (!any) __nanosleep(2000);
+    }
+    if (want_s) { rs.finish(d.seq, total, dig); if (!md5_equal(dig, d.md5[1]) && *status == 0) *status = -9; }
+    if (want_q) { rq.finish(d.qual, total, dig); if (!md5_equal(dig, d.md5[2]) && *status == 0) *status = -10; }
+}
+
 template <int QLEVEL>
-__global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 seqmask) {
+__global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 seqmask, int inline_md5) {
     constexpr int qlevel = QLEVEL;
     __shared__ __align__(16) MainSmem sm;
     DecBlock &d = db[blockIdx.x];
     int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u64 pol = wid == 2 ? l2_policy_stream() : l2_policy_keep();
-    if (threadIdx.x == 0) { sm.qprog = 0; sm.side_err = 0; }
+    if (threadIdx.x == 0) { sm.qprog = 0; sm.sprog = 0; sm.side_err = 0; }
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm.rlut[i] = recip_est(i < 2 ? 2 : i);
     __syncthreads();
     if (d.status != 0) return;
@@ -508,7 +596,10 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
     const u32 *seqoff = d.seqoff;
     const i32 *seqlen = d.seqlen;
     if (wid == 0) {                                            // names (decompressName @0x428ca0)
-        if (id_rule) { if (lane == 0) d.idbytes = 0; return; }   // rule-based IDs (IDProcess::decodeIDS) are regenerated by the host layer from the tag-5 payload
+        if (id_rule) {                                         // rule-based IDs (IDProcess::decodeIDS) are regenerated by the host layer from the tag-5 payload
+            if (lane == 0) { d.idbytes = 0; if (inline_md5) md5_chase(d, &sm.qprog, &sm.sprog, seqoff, nreads, id_rule); }
+            return;
+        }
         for (int i = lane; i < 1024; i += 32) sm.ns.last[i] = ' ';
         __syncwarp();
         int lnl = 0, lpl = 0, lsl = 0;
@@ -527,6 +618,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         }
         if (lane == 0) d.idbytes = o;
         SQ_TICK("names");
+        if (inline_md5 && lane == 0) md5_chase(d, &sm.qprog, &sm.sprog, seqoff, nreads, id_rule);
     } else if (wid == 1) {                                     // qualities (decompressQual @0x42aa40, decode_qual @0x42a750)
         RcDecW rc;
         rc.start(rec + d.off[7], rec + d.off[7] + d.len[7]);
@@ -607,6 +699,10 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         P.init();
         u32 i_mq = 0, i_ch = 0, i_pos = 0;
         for (u32 r = 0; r < nreads; r++) {
+            if (inline_md5 && r && (r & 15) == 0) {             // reads [0, r) are final: let the MD5 chaser have them
+                __threadfence_block();
+                if (lane == 0) sm.sprog = r;
+            }
             u8 *seq = seqout + seqoff[r];
             int len = seqlen[r];
             u32 last = 0x7616c7u & seqmask;
@@ -651,6 +747,10 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
             }
         }
         asm volatile("cp.async.wait_all;\n" ::: "memory");
+        if (inline_md5) {
+            __threadfence_block();
+            if (lane == 0) sm.sprog = nreads;
+        }
         SQ_TICK("seq");
     }
 }
@@ -707,10 +807,15 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
         }
     }
     k_dec_len<<<B, 32, 0, st>>>(w.db);
-    if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
-    else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
-    else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask);
+    // The MD5s are verified inside k_dec_main (lane 0 of the names warp chases the other two warps: -0.7 s of
+    // 10.7 s on the full job); SQ_DEC_INLINE_MD5=0 brings back the separate k_dec_md5 pass.
+    static int inl = -1;
+    if (inl < 0) { const char *e = getenv("SQ_DEC_INLINE_MD5"); inl = e ? atoi(e) != 0 : 1; }
+    const int inline_md5 = (w.md5 && inl) ? 1 : 0;
+    if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5);
+    else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5);
+    else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5);
     *launches += 2;
-    if (w.md5) { k_dec_md5<<<cdivd(3ull * B, 32), 32, 0, st>>>(w.db, B, w.id_rule); *launches += 1; }
+    if (w.md5 && !inline_md5) { k_dec_md5<<<cdivd(3ull * B, 32), 32, 0, st>>>(w.db, B, w.id_rule); *launches += 1; }
     return cudaGetLastError();
 }
