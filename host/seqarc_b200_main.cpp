@@ -357,6 +357,7 @@ static int do_decompress(const Opt &o) {
 int main(int argc, char **argv) {
     Opt o;
     read_config(o);
+    std::vector<std::string> pos;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto val = [&]() -> std::string { if (i + 1 >= argc) die("missing value after " + a); return argv[++i]; };
@@ -372,11 +373,39 @@ int main(int argc, char **argv) {
         else if (a == "-l") { o.lossy = true; o.lossy_r = atof(val().c_str()); }
         else if (a == "-g") o.device = atoi(val().c_str());
         else if (a == "-b") o.batch = atoi(val().c_str());
-        else if (a == "-h") { printf("usage: seqarc_b200 -c [ref.fa] -1 a.fq [-2 b.fq] -o out [-l r] [-n] [-f] | -d [ref.fa] in.arc -o out [-f]\n"); return 0; }
-        else if (a[0] != '-') { if (!o.arc.empty()) o.ref = o.arc; o.arc = a; }   // [ref.fa] precedes the archive
+        else if (a == "-h") { printf("usage: seqarc_b200 -c [ref.fa] -1 a.fq [-2 b.fq] -o out [-l r] [-n] [-f]   (or: -c [ref.fa] a.fq [b.fq] out)\n       seqarc_b200 -d [ref.fa] in.arc -o out [-f]                            (or: -d [ref.fa] in.arc out)\n"); return 0; }
+        else if (a[0] != '-') pos.push_back(a);
         else die("unknown option " + a);
     }
-    if (o.compress && o.ref.empty()) { o.ref = o.arc; o.arc.clear(); }            // -c [ref.fa] -1 ... -o ...
+    // positional forms of the reference CLI:
+    //   -c [options] [ref.fa] <input_file> [input_file2] <compress_prefix>      (or -1 / -2 / -o)
+    //   -d [options] [ref.fa] <x.arc> [fastq_prefix]
+    auto ends_with = [](const std::string &x, const char *suf) { size_t n = strlen(suf); return x.size() >= n && x.compare(x.size() - n, n, suf) == 0; };
+    auto is_fasta = [&](const std::string &x) { return ends_with(x, ".fa") || ends_with(x, ".fasta") || ends_with(x, ".fna"); };
+    if (o.compress) {
+        size_t k = 0;
+        if (k < pos.size() && is_fasta(pos[k])) o.ref = pos[k++];
+        std::vector<std::string> rest(pos.begin() + k, pos.end());
+        if (o.in1.empty()) {                       // inputs (and the prefix, unless -o) are positional
+            size_t need_out = o.out.empty() ? 1 : 0;
+            if (rest.size() == 1 + need_out) o.in1 = rest[0];
+            else if (rest.size() == 2 + need_out) { o.in1 = rest[0]; o.in2 = rest[1]; }
+            else if (!rest.empty()) die("cannot tell inputs from the output prefix (see -h)");
+            if (need_out && !rest.empty()) o.out = rest.back();
+        } else if (rest.size() == 1 && o.out.empty()) o.out = rest[0];
+        else if (!rest.empty()) die("unexpected argument " + rest[0]);
+    } else if (o.decompress) {
+        size_t k = 0;
+        if (k + 1 < pos.size() && !ends_with(pos[k], ".arc")) o.ref = pos[k++];
+        if (k < pos.size()) o.arc = pos[k++];
+        if (k < pos.size() && o.out.empty()) o.out = pos[k++];
+        if (k < pos.size()) die("unexpected argument " + pos[k]);
+    }
+    if (getenv("SQ_CLI_PARSE_ONLY")) {             // argument handling is testable without a GPU
+        printf("mode=%s ref=%s in1=%s in2=%s arc=%s out=%s lossy=%d md5=%d\n", o.compress ? "c" : o.decompress ? "d" : "-", o.ref.c_str(),
+               o.in1.c_str(), o.in2.c_str(), o.arc.c_str(), o.out.c_str(), (int)o.lossy, (int)o.md5);
+        return 0;
+    }
     try {
         if (o.compress && !o.in1.empty() && !o.out.empty()) return do_compress(o);
         if (o.decompress && !o.arc.empty() && !o.out.empty()) return do_decompress(o);

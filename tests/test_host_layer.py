@@ -203,3 +203,22 @@ def test_mixed_plus_lines_are_refused(hl):
         open(q, "wb").write(plus_lines(t))
         assert hl.sqh_cut_blocks(q.encode(), None, 50 << 20, nr.ctypes.data, s1.ctypes.data, s2.ctypes.data, cap) == 1
         assert int(nr[0]) == 4000 and int(s1[0]) == len(plus_lines(t))
+
+
+def test_cli_argument_forms():
+    """Both forms of the reference command line: -1 / -2 / -o, or positional [ref.fa] inputs prefix."""
+    import subprocess
+    cli = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
+    env = dict(os.environ, SQ_CLI_PARSE_ONLY="1")
+
+    def parse(args):
+        out = subprocess.run([cli] + args.split(), env=env, capture_output=True, text=True, cwd=tempfile.gettempdir())
+        assert out.returncode == 0, out.stderr
+        return dict(kv.split("=", 1) for kv in out.stdout.split())
+
+    assert parse("-c -1 a.fq -2 b.fq -o out") == dict(mode="c", ref="", in1="a.fq", in2="b.fq", arc="", out="out", lossy="0", md5="1")
+    assert parse("-c -t 16 -f ref.fa a.fq b.fq out -l 1.15") == dict(mode="c", ref="ref.fa", in1="a.fq", in2="b.fq", arc="", out="out", lossy="1", md5="1")
+    assert parse("-c a.fq.gz out -n") == dict(mode="c", ref="", in1="a.fq.gz", in2="", arc="", out="out", lossy="0", md5="0")
+    assert parse("-c ref.fasta -1 a.fq -o out")["ref"] == "ref.fasta"
+    assert parse("-d x.arc -o back") == dict(mode="d", ref="", in1="", in2="", arc="x.arc", out="back", lossy="0", md5="1")
+    assert parse("-d -t 8 ref.fa x.arc back") == dict(mode="d", ref="ref.fa", in1="", in2="", arc="x.arc", out="back", lossy="0", md5="1")
