@@ -63,6 +63,11 @@ CASES = [
     dict(name="bgi_pe100", src=dict(kind="bgi_pe100", n_templates=1200, seed=13), pe=True, opts=[], config=None),
     dict(name="old_illumina_pe100", src=dict(kind="old_illumina_pe100", n_templates=1200, seed=14), pe=True, opts=[], config=None),
     dict(name="sra_len_se100", src=dict(kind="sra_len_se100", n_templates=2500, seed=15), pe=False, opts=[], config=None),
+    # the extreme base-context orders: Slevel 0 (order 7) and Slevel 5 (order 12)
+    dict(name="illumina_pe150_s0", src=dict(kind="illumina_pe150", n_templates=700, seed=23, n_rate=0.001), pe=True, opts=[],
+         config={"Slevel": 0}),
+    dict(name="illumina_pe150_s5", src=dict(kind="illumina_pe150", n_templates=700, seed=24, n_rate=0.001), pe=True, opts=[],
+         config={"Slevel": 5}),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
