@@ -174,6 +174,18 @@ extern "C" int sq_load_model(sq_ctx *c, const uint8_t *blob, uint64_t len) {
     CUDA_OK(c, cudaMalloc((void **)&c->d_model, len));
     CUDA_OK(c, cudaMemcpy(c->d_model, blob, len, cudaMemcpyHostToDevice));
     c->model_len = len;
+    // base contexts: the training rule (@0x421fb0: halve above 253, then one increment) bounds every context's
+    // total by 254; anything else is not a SaveModelToMem blob
+    int bad = 0, *d_flag = nullptr;
+    CUDA_OK(c, cudaMalloc((void **)&d_flag, sizeof(int)));
+    cudaError_t e = sqk_check_seqsnap(c->d_model + c->snap_name_bytes(), c->nseq(), d_flag, &bad, c->stream);
+    cudaFree(d_flag);
+    CUDA_OK(c, e);
+    if (bad) {
+        cudaFree(c->d_model); c->d_model = nullptr; c->model_len = 0;
+        c->err = "model snapshot: a base context sums above 254 (corrupt snapshot)";
+        return SQ_ERR_FORMAT;
+    }
     return SQ_OK;
 }
 

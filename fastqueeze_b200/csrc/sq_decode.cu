@@ -146,16 +146,6 @@ __global__ void __launch_bounds__(256) k_init_wm(DecBlock *db, int which, u32 nm
         mp[EPL * 32 + lane] = base | (tot << 16);
     }
 }
-__global__ void k_init_seqtab(DecBlock *db, u64 bytes, const u8 *snap) {
-    int b = blockIdx.y;
-    if (db[b].status != 0) return;
-    u32 *t = (u32 *)db[b].seqtab;
-    const u32 *s = (const u32 *)snap;
-    u64 n = bytes / 4;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-        t[i] = s ? s[i] : 0x03030303u;
-}
-
 // decodeSymbol (inlined e.g. @0x42a7d0-0x42a960) on a warp model, in three phases so that the
 // caller can issue the NEXT model's loads between the search and the write-back of this one.
 template <int EPL> struct WReg { u32 w[EPL]; u32 bt; };
@@ -295,6 +285,232 @@ SQ_D u32 wm_decode(u32 *mp, RcDecW &rc, int lane, u64 pol) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Quality models of the decoder: "Q4" layout.  A SIMPLE_MODEL<95> is 32 lanes x 16 bytes (512 B, one
+// 128-bit load / store per lane); lane l owns entries 3l, 3l+1, 3l+2 (slot 95 is a dummy of frequency 0):
+//   x = c1 | c2 << 16      inclusive cumulative frequencies through the lane's 1st / 2nd entry
+//   y = c3 | tot << 16     ... through its 3rd entry; TotFreq
+//   z = floor((2^32 - 1) / tot)   the reciprocal the division range / tot needs -- kept in the model so that
+//                                 no int->float->rcp->int conversion sits on the symbol chain
+//   w = s0 | s1 << 8 | s2 << 16 | (BubCnt & 15) << 24
+// Cumulative sums are absolute (they include the lower lanes), so the search needs no prefix: lane l "hits"
+// when code < c3_l * r, hits are monotone in l, and the symbol's lane is the number of lanes that miss.
+// The update adds 8 to every cumulative sum at or above the symbol -- one packed add per word.
+struct RcWin;
+SQ_D u32 recip32(u32 d) { return 0xffffffffu / (d ? d : 1u); }     // in [2^32/d - 1, 2^32/d]: mulhi(n, .) is floor(n/d) or one less
+
+template <int N>
+__global__ void __launch_bounds__(256) k_init_q4(DecBlock *db, u32 nmodels, const u8 *snap, u32 snapstride) {
+    static_assert(N <= 96, "three entries per lane");
+    int b = blockIdx.y;
+    if (db[b].status != 0) return;
+    uint4 *tab = (uint4 *)db[b].qualtab;
+    int lane = threadIdx.x & 31;
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 m = warp; m < nmodels; m += nwarps) {
+        const u8 *s = snap ? snap + (u64)m * snapstride : nullptr;
+        u32 tot = N, bub = 0;
+        if (s) { tot = get_u32le(s) & 0xffffu; bub = get_u32le(s + 4) & 15u; }
+        u32 f[3], sy[3], T = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            int slot = lane * 3 + i;
+            sy[i] = (u32)slot & 0xff; f[i] = slot < N ? 1 : 0;
+            if (s && slot < N) { const u8 *q = s + 8 + 3 * slot; sy[i] = q[0]; f[i] = (u32)(q[1] | (q[2] << 8)); }
+            T += f[i];
+        }
+        u32 base = warp_incl_scan_d(T, lane) - T;
+        u32 c1 = (base + f[0]) & 0xffffu, c2 = (base + f[0] + f[1]) & 0xffffu, c3 = (base + T) & 0xffffu;
+        uint4 v;
+        v.x = c1 | (c2 << 16);
+        v.y = c3 | (tot << 16);
+        v.z = recip32(tot);
+        v.w = sy[0] | (sy[1] << 8) | (sy[2] << 16) | (bub << 24);
+        tab[(u64)m * 32 + lane] = v;
+    }
+}
+
+// Range decoder with a byte window fed by aligned 32-bit loads issued one refill ahead: no load and no
+// byte assembly sits on the symbol chain (RangeCoder decode @0x429760-0x429880).
+struct RcWin {
+    u64 low;
+    u32 range, code;
+    u64 win;                 // the next bytes of the stream, first byte on top
+    int avail;               // valid bytes in win
+    const u32 *wp, *wend;    // next aligned word to fetch / first word past the stream
+    u32 nxt;                 // the word fetched ahead
+    SQ_D void fetch() { nxt = wp < wend ? __ldg(wp) : 0u; wp++; }
+    SQ_D void refill() {     // needs avail <= 4
+        win |= (u64)__byte_perm(nxt, 0, 0x0123) << (32 - 8 * avail);
+        avail += 4;
+        fetch();
+    }
+    SQ_D u32 get() {
+        u32 b = (u32)(win >> 56);
+        win <<= 8;
+        avail--;
+        if (avail <= 4) refill();
+        return b;
+    }
+    SQ_D void start(const u8 *i, const u8 *e) {
+        low = 0; range = 0xffffffffu; code = 0;
+        uintptr_t a = (uintptr_t)i;
+        int skip = (int)(a & 3);
+        wp = (const u32 *)(a - skip);
+        wend = (const u32 *)(((uintptr_t)e + 3) & ~(uintptr_t)3);
+        fetch();
+        win = (u64)__byte_perm(nxt, 0, 0x0123) << (32 + 8 * skip);
+        avail = 4 - skip;
+        fetch();
+        refill();
+        for (int k = 0; k < 8; k++) code = (code << 8) | get();
+    }
+    // `range` already holds range / tot.  A symbol renormalises by at most two bytes in the common case
+    // (range / tot >= 2^8); the carry-less range adjustment needs bits 32..47 of low all ones, which sends
+    // us to the exact loop.
+    SQ_D void decode(u32 cum, u32 freq) {
+        u32 t = cum * range;
+        low += t;
+        code -= t;
+        range *= freq;
+        if (range >= (1u << 24)) return;
+        if ((~(u32)(low >> 32) & 0xffffu) == 0 || range < (1u << 8)) {
+            for (int guard = 0; guard < 16 && range < (1u << 24); guard++) {
+                if ((low ^ (low + range)) >> 56) range = (((u32)low) | 0xffffffu) - (u32)low;
+                code = (code << 8) | get();
+                range <<= 8;
+                low <<= 8;
+            }
+            return;
+        }
+        u32 sh = range < (1u << 16) ? 16 : 8;
+        code = __funnelshift_l((u32)(win >> 32), code, sh);
+        win <<= sh;
+        avail -= (int)(sh >> 3);
+        range <<= sh;
+        low <<= sh;
+        if (avail <= 4) refill();
+    }
+};
+
+SQ_D uint4 q4_ld(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+SQ_D void q4_st(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SQ_D u32 shl_clamp(u32 v, u32 n) { u32 r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+
+// rare: TotFreq passed 0xffe0 (@0x4222b7): halve every frequency, rebuild the cumulative sums
+SQ_D void q4_halve(uint4 &M, int lane) {
+    u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
+    u32 c0 = __shfl_up_sync(FULL, c3, 1);
+    c0 = lane ? c0 : 0u;
+    u32 f0 = (c1 - c0) & 0xffffu, f1 = (c2 - c1) & 0xffffu, f2 = (c3 - c2) & 0xffffu;
+    f0 -= f0 >> 1; f1 -= f1 >> 1; f2 -= f2 >> 1;
+    u32 T = f0 + f1 + f2;
+    u32 inc = warp_incl_scan_d(T, lane);
+    u32 base = inc - T;
+    u32 tot = __shfl_sync(FULL, inc, 31);
+    M.x = ((base + f0) & 0xffffu) | ((base + f0 + f1) << 16);
+    M.y = (inc & 0xffffu) | (tot << 16);
+}
+// every 16th symbol of a model (@0x4222d3-0x4222f1): swap the coded entry with its predecessor when its
+// frequency is strictly greater.  kl / li locate the coded entry (li is only meaningful on lane kl).
+SQ_D void q4_bubble(uint4 &M, int kl, int li, int lane) {
+    u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
+    u32 c0 = __shfl_up_sync(FULL, c3, 1);
+    c0 = lane ? c0 : 0u;
+    u32 up_f2 = __shfl_up_sync(FULL, c3 - c2, 1);          // frequency of the previous lane's last entry
+    u32 up_s2 = __shfl_up_sync(FULL, (M.w >> 16) & 0xffu, 1);
+    u32 fk = li == 0 ? c1 - c0 : (li == 1 ? c2 - c1 : c3 - c2);
+    u32 fp = li == 0 ? up_f2 : (li == 1 ? c1 - c0 : c2 - c1);
+    bool mine = lane == kl;
+    bool dosw = mine && (kl * 3 + li > 0) && fk > fp;
+    u32 swb = __ballot_sync(FULL, dosw);
+    if (!swb) return;
+    int lik = __shfl_sync(FULL, li, kl);
+    u32 fkb = __shfl_sync(FULL, fk, kl);
+    u32 s0b = __shfl_sync(FULL, M.w & 0xffu, kl);
+    if (lik == 1) {
+        if (mine) { c1 = c0 + fk; M.x = c1 | (c2 << 16); M.w = __byte_perm(M.w, 0, 0x3201); }
+    } else if (lik == 2) {
+        if (mine) { c2 = c1 + fk; M.x = c1 | (c2 << 16); M.w = __byte_perm(M.w, 0, 0x3120); }
+    } else {
+        // the predecessor is the last entry of lane kl - 1: its inclusive sum becomes c2 + f_k there
+        if (mine) M.w = (M.w & 0xffffff00u) | up_s2;
+        if (lane == kl - 1) { M.y = (M.y & 0xffff0000u) | ((c2 + fkb) & 0xffffu); M.w = (M.w & 0xff00ffffu) | (s0b << 16); }
+    }
+}
+
+// One quality symbol (decode_qual @0x42a750; decodeSymbol inlined @0x42a7d0-0x42a960).  M is the model of
+// context `last` (this lane's 16 bytes).  The next model's load is issued as soon as the symbol is known;
+// the coder step, the output byte and this model's update + write-back fill its latency.
+// SAT: delta has reached 56 in this read (it only grows), so its context bits are constant.
+template <int QLEVEL, bool SAT>
+SQ_D u32 q4_step(uint4 &M, u32 &last, RcWin &rc, uint4 *tab, u8 *qout, int i, int len, u32 &q1, u32 &q2, u32 &delta, int lane) {
+    const u32 tot = M.y >> 16;
+    const u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
+    u32 c0 = __shfl_up_sync(FULL, c3, 1);
+    c0 = lane ? c0 : 0u;
+    // r = range / tot
+    u32 r = __umulhi(rc.range, M.z);
+    u32 rem = rc.range - r * tot;
+    r += (rem >= tot) ? 1u : 0u;
+    const u32 code = rc.code;
+    const u32 miss = __ballot_sync(FULL, code >= c3 * r);
+    const int kl = __popc(miss);                          // hits are monotone in the lane index
+    const bool p1 = code >= c1 * r, p2 = code >= c2 * r;   // monotone: p2 implies p1
+    const int li = (int)p1 + (int)p2;
+    const u32 cex = p2 ? c2 : (p1 ? c1 : c0);
+    const u32 cnx = p2 ? c3 : (p1 ? c2 : c1);
+    u32 A = cex | ((cnx - cex) << 16);
+    const u32 sy = __byte_perm(M.w, 0, 0x4440u | (u32)li);
+    const u32 qq = __shfl_sync(FULL, sy, kl);
+    A = __shfl_sync(FULL, A, kl);
+    // context of the next symbol (encode_qual @0x422474-0x422505); 0 opens the next read
+    const bool more = i + 1 < len;
+    const u32 amax = (q1 > q2 ? q1 : q2) << 6;
+    u32 K = 0;
+    if (QLEVEL > 1) K |= (u32)(q1 == q2) << 12;
+    if (QLEVEL > 2) K |= (i <= 111) ? (u32)((i + 15) & 0x78) << 13 : 0xf0000u;
+    u32 nl;
+    if (SAT || QLEVEL == 1) {
+        if (QLEVEL > 1) K |= (56u & 0xf8u) << 10;
+        const u32 mk = more ? 0xfffu : 0u;
+        K = more ? K : 0u;
+        nl = ((amax + qq) & mk) | K;
+    } else {
+        int dd = (int)q1 - (int)qq;
+        u32 d2 = delta + (u32)(dd > 0 ? dd : 0);
+        nl = (((amax + qq) & 0xfffu) | K | (((d2 < 56 ? d2 : 56u) & 0xf8u) << 10)) & (more ? 0xffffffffu : 0u);
+        delta = d2;
+    }
+    const uint4 Mn = q4_ld(tab + (u64)nl * 32);
+    // ---- off the symbol chain from here
+    rc.range = r;
+    rc.decode(A & 0xffffu, A >> 16);
+    if (lane == 0) qout[i] = (u8)(qq + 33);
+    // Freq += 8, TotFreq += 8 (@0x4222a0): every cumulative sum at or above the coded entry moves
+    const bool ge = lane >= kl;
+    const u32 lik = lane == kl ? (u32)li : 0u;
+    M.x += ge ? shl_clamp(0x00080008u, 16u * lik) : 0u;
+    M.y += (ge ? 8u : 0u) + (8u << 16);
+    u32 bub = ((M.w >> 24) + 1) & 15u;
+    M.w = (M.w & 0x00ffffffu) | (bub << 24);
+    if (tot + 8 > 0xffe0u) q4_halve(M, lane);
+    if (bub == 0) q4_bubble(M, kl, li, lane);
+    M.z = recip32(M.y >> 16);
+    q4_st(tab + (u64)last * 32, M);
+    const bool same = nl == last;
+    M.x = same ? M.x : Mn.x; M.y = same ? M.y : Mn.y; M.z = same ? M.z : Mn.z; M.w = same ? M.w : Mn.w;
+    last = nl;
+    q2 = q1; q1 = qq;
+    return qq;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Len stream (decompressLen_short @0x428170 / decode_len_short @0x427ca0) + read offsets.
 // The reference keeps last_len across blocks per decoder instance; a zero-length
 // read therefore decodes to "whatever came before".  Here last_len starts at 0 for every block.
@@ -376,33 +592,56 @@ SQ_D int decode_name(u32 *nametab, RcDecW &rc, u8 *name_out, u64 room, NameSmem 
     return n;
 }
 
-// one base (inlined four times in decode_seq @0x4296b0); whole warp, uniform.
-// The 4^SQ_LOOK contexts reachable SQ_LOOK bases ahead are contiguous in the table: every step the
-// warp copies them asynchronously (cp.async, L2 -> shared) into an 8-slot ring and reads the counters
-// it needs NOW from the slot filled SQ_LOOK steps ago, so the table's L2 / HBM latency is off the
-// symbol chain.  SQ_LOOK = 2 (64 B per base): at ~600 cycles per base two steps cover an HBM round
-// trip; four steps (1 KiB per base) measured 6.9 TB of DRAM reads per 14 GB job for no gain.
-// Counters updated during the look-ahead window are forwarded from a 4-entry log.  Every lane stores
-// the updated counters (same value, same address): each lane later reads its own store, and
-// __syncwarp orders it before the other lanes' later copies.
-#define SQ_LOOK 2
+// ---------------------------------------------------------------------------------------------
+// Base model of the decoder (BASE_MODEL<uint8_t>, decode inlined four times in decode_seq @0x4296b0).
+// Decoder-private context word: c1 | c2 << 8 | c3 << 16 | tot << 24 -- the inclusive cumulative counts of
+// A, A+C, A+C+G and the total (<= 254: a context is halved when its total passes 253 BEFORE a base is coded,
+// @0x421fb0, then one counter is incremented).  Thresholds, the coded interval and the update (+1 on every
+// byte at or above the base) come straight out of the word without unpacking four counters.
+// The 4^SQ_LOOK contexts reachable SQ_LOOK bases ahead are contiguous in the table: every step the warp
+// copies them asynchronously (cp.async, L2 -> shared, bypassing L1) into an 8-slot ring and reads the word it
+// needs NOW from the slot filled SQ_LOOK steps ago, so the table's HBM latency (the table is 4 MiB per block,
+// random access: it never stays in cache) is off the symbol chain.  Words updated inside the look-ahead
+// window are forwarded from a register log.  Every lane stores the updated word (same value, same address):
+// each lane's later copies are ordered after its own stores.
+#ifndef SQ_LOOK
+#define SQ_LOOK 3
+#endif
 #define SQ_LOOK_N (1 << (2 * SQ_LOOK))          // contexts per ring slot
+#define SQ_LOG 4                                // forwarded updates (>= SQ_LOOK + 1)
+static_assert(SQ_LOOK >= 2 && SQ_LOOK <= 3, "ring copy uses 16-byte pieces on up to 16 lanes");
 struct SeqPipe {
     u32 step;
-    u32 lc0, lc1, lc2, lc3, lv0, lv1, lv2, lv3;      // last four updated (context, counters), 0 = newest
+    u32 lc0, lc1, lc2, lc3, lv0, lv1, lv2, lv3;      // last four updated (context, word), 0 = newest
     SQ_D void init() { step = 0; lc0 = lc1 = lc2 = lc3 = 0xffffffffu; lv0 = lv1 = lv2 = lv3 = 0; }
 };
 
-SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane, u64 pol) {
+__global__ void k_init_seqtab(DecBlock *db, u64 nctx, const u8 *snap) {
+    int b = blockIdx.y;
+    if (db[b].status != 0) return;
+    u32 *t = (u32 *)db[b].seqtab;
+    const u32 *s = (const u32 *)snap;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nctx; i += (u64)gridDim.x * blockDim.x) {
+        u32 v = s ? s[i] : 0x03030303u;
+        u32 s0 = v & 0xff, s1 = (v >> 8) & 0xff, s2 = (v >> 16) & 0xff, s3 = v >> 24;
+        u32 c1 = s0, c2 = c1 + s1, c3 = c2 + s2, tot = c3 + s3;     // <= 254 for every snapshot sq_load_model accepts
+        t[i] = (c1 & 0xff) | ((c2 & 0xff) << 8) | ((c3 & 0xff) << 16) | ((tot & 0xff) << 24);
+    }
+}
+// a snapshot whose base contexts sum above 254 cannot come from the reference's training (same update rule)
+__global__ void k_check_seqsnap(const u32 *snap, u64 nctx, int *bad) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nctx; i += (u64)gridDim.x * blockDim.x) {
+        u32 v = snap[i];
+        if ((v & 0xff) + ((v >> 8) & 0xff) + ((v >> 16) & 0xff) + (v >> 24) > 254u) *bad = 1;
+    }
+}
+
+SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcWin &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane, u64 pol) {
     if (lane < SQ_LOOK_N / 4) {
         u32 basec = (last << (2 * SQ_LOOK)) & mask;
         const u8 *src = seqtab + ((u64)basec << 2) + lane * 16;
         u32 dst = (u32)__cvta_generic_to_shared(ring + ((P.step + SQ_LOOK) & 7) * SQ_LOOK_N + lane * 4);
-#if SQ_L2_HINTS
         asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(pol) : "memory");
-#else
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-#endif
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     u32 *S4 = (u32 *)(seqtab + (u64)last * 4);
@@ -412,27 +651,32 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcDecW &rc, u32 &la
         __syncwarp();
         x = ring[(P.step & 7) * SQ_LOOK_N + (last & (SQ_LOOK_N - 1))];
     } else {
-        x = ld_hint<(SQ_L2_HINTS != 0)>(S4, pol);
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(x) : "l"(S4), "l"(pol) : "memory");
     }
-    if (P.lc3 == last) x = P.lv3;
-    if (P.lc2 == last) x = P.lv2;
-    if (P.lc1 == last) x = P.lv1;
-    if (P.lc0 == last) x = P.lv0;
-    u32 S0 = x & 0xff, S1 = (x >> 8) & 0xff, S2 = (x >> 16) & 0xff, S3 = x >> 24;
-    u32 tot = S0 + S1 + S2 + S3;
-    if (tot > 253) { S0 -= S0 >> 1; S1 -= S1 >> 1; S2 -= S2 >> 1; S3 -= S3 >> 1; tot = S0 + S1 + S2 + S3; }
-    u32 r = div_est(rc.range, tot, rlut[tot]);
+    // forwarding: resolved while the ring read is in flight
+    const bool h0 = P.lc0 == last, h1 = P.lc1 == last, h2 = P.lc2 == last, h3 = P.lc3 == last;
+    const u32 fv = h0 ? P.lv0 : (h1 ? P.lv1 : (h2 ? P.lv2 : P.lv3));
+    x = (h0 || h1 || h2 || h3) ? fv : x;
+    u32 tot = x >> 24;
+    if (tot > 253) {                                 // rare: halve the four counters (S -= S >> 1)
+        u32 s0 = x & 0xff, s1 = ((x >> 8) - x) & 0xff, s2 = ((x >> 16) - (x >> 8)) & 0xff, s3 = (tot - (x >> 16)) & 0xff;
+        s0 -= s0 >> 1; s1 -= s1 >> 1; s2 -= s2 >> 1; s3 -= s3 >> 1;
+        u32 c2 = s0 + s1, c3 = c2 + s2;
+        tot = (c3 + s3) & 0xff;
+        x = s0 | ((c2 & 0xff) << 8) | ((c3 & 0xff) << 16) | (tot << 24);
+    }
+    u32 r = __umulhi(rc.range, rlut[tot]);
+    u32 rem = rc.range - r * tot;
+    r += (rem >= tot) ? 1u : 0u;
+    const u32 code = rc.code;
+    const u32 c1 = x & 0xff, c2 = (x >> 8) & 0xff, c3 = (x >> 16) & 0xff;
+    const u32 b = (u32)(code >= c1 * r) + (u32)(code >= c2 * r) + (u32)(code >= c3 * r);
+    const u32 sh = 8 * b;
+    const u32 cum = ((x << 8) >> sh) & 0xff, cnx = (x >> sh) & 0xff;
     rc.range = r;
-    u32 code = rc.code;
-    u32 c1 = S0, c2 = S0 + S1, c3 = c2 + S2;
-    u32 b = (u32)(code >= c1 * r) + (u32)(code >= c2 * r) + (u32)(code >= c3 * r);
-    u32 cum = b == 0 ? 0u : (b == 1 ? c1 : (b == 2 ? c2 : c3));
-    u32 f = b == 0 ? S0 : (b == 1 ? S1 : (b == 2 ? S2 : S3));
-    rc.decode(cum, f);
-    u32 packed = S0 | (S1 << 8) | (S2 << 16) | (S3 << 24);
-    u32 inc = 1u << (8 * b);
-    u32 nv = (f == 255) ? (packed & ~(0xffu << (8 * b))) : packed + inc;     // (S[b] + 1) & 0xff
-    st_hint<(SQ_L2_HINTS != 0)>(S4, nv, pol);
+    rc.decode(cum, (cnx - cum) & 0xff);
+    const u32 nv = x + (0x01010101u << sh);          // S[b]++: every cumulative byte at or above b
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(S4), "r"(nv), "l"(pol) : "memory");
     __syncwarp();
     P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
     P.step++;
@@ -475,7 +719,7 @@ struct KModelD {
 };
 struct MainSmem {
     u32 ring[8 * SQ_LOOK_N];   // base-model candidate ring of the seq warp (8 slots x 4^SQ_LOOK contexts)
-    u32 rlut[1024];            // reciprocal estimates of every possible base-model total (<= 1020)
+    u32 rlut[256];             // reciprocal of every possible base-model total (<= 255)
     NameSmem ns;
     SmModel<2> tip;
     SmModel<11> ch;
@@ -582,7 +826,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
     int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const u64 pol = wid == 2 ? l2_policy_stream() : l2_policy_keep();
     if (threadIdx.x == 0) { sm.qprog = 0; sm.sprog = 0; sm.side_err = 0; }
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm.rlut[i] = recip_est(i < 2 ? 2 : i);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.rlut[i] = recip32(i);
     __syncthreads();
     if (d.status != 0) return;
 #ifdef SQ_DEBUG_TIMING
@@ -620,39 +864,23 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         SQ_TICK("names");
         if (inline_md5 && lane == 0) md5_chase(d, &sm.qprog, &sm.sprog, seqoff, nreads, id_rule);
     } else if (wid == 1) {                                     // qualities (decompressQual @0x42aa40, decode_qual @0x42a750)
-        RcDecW rc;
+        RcWin rc;
         rc.start(rec + d.off[7], rec + d.off[7] + d.len[7]);
-        u32 *tab = d.qualtab;
+        uint4 *tab = (uint4 *)d.qualtab + lane;
         u8 *qual = d.qual;
-        WReg<3> R;
         u32 last = 0;
-        wm_load(R, tab, lane, pol);                            // context 0 opens every read
+        uint4 M = q4_ld(tab);                                  // context 0 opens every read
         for (u32 r = 0; r < nreads; r++) {
             u8 *q = qual + seqoff[r];
-            int len = seqlen[r];
-            u32 delta = 5, q1 = 0, q2 = 0;
-            for (int i = 0; i < len; i++) {
-                int kl, li;
-                u32 cex, freq;
-                u32 qq = wm_find<95, 3>(R, rc, lane, kl, li, cex, freq);
-                u32 nlast = 0;
-                bool term = qq == 94;
-                if (!term) {
-                    if (lane == 0) q[i] = (u8)(qq + 33);
-                    if (q1 > qq) delta += q1 - qq;
-                    if (i + 1 < len) nlast = qual_ctx(qq, q1, q2, delta, qlevel, i);
-                    q2 = q1; q1 = qq;
-                }
-                // the next model's rows are requested before this model is written back
-                u32 *mp = tab + (u64)last * WQ_STRIDE;
-                WReg<3> Rn;
-                bool same = nlast == last;
-                if (!same) wm_load(Rn, tab + (u64)nlast * WQ_STRIDE, lane, pol);
-                rc.decode(cex, freq);
-                wm_update_store<95, 3>(mp, R, kl, li, lane, pol);
-                if (!same) R = Rn;
-                last = nlast;
-                if (term) { for (int t = i + lane; t < len; t += 32) q[t] = '#'; break; }
+            const int len = seqlen[r];
+            u32 delta = 5, q1 = 0, q2 = 0, qq = 0;
+            int i = 0;
+            if (qlevel > 1)
+                for (; i < len && delta < 56 && qq != 94; i++) qq = q4_step<QLEVEL, false>(M, last, rc, tab, q, i, len, q1, q2, delta, lane);
+            for (; i < len && qq != 94; i++) qq = q4_step<QLEVEL, true>(M, last, rc, tab, q, i, len, q1, q2, delta, lane);
+            if (qq == 94) {                                    // the rest of the read is '#' (@0x42a9a0); context 0 opens the next read
+                for (int t = i - 1 + lane; t < len; t += 32) q[t] = '#';
+                if (last != 0) { M = q4_ld(tab); last = 0; }
             }
             if ((r & 15) == 15 || r + 1 == nreads) {
                 __syncwarp();
@@ -693,7 +921,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         const u32 *d_cnt = d.d_cnt, *d_pos = d.d_pos;
         u8 *seqtab = d.seqtab, *seqout = d.seq;
         const u8 *qualbuf = d.qual;
-        RcDecW rc;
+        RcWin rc;
         rc.start(rec + d.off[6], rec + d.off[6] + d.len[6]);
         SeqPipe P;
         P.init();
@@ -774,12 +1002,22 @@ __global__ void __launch_bounds__(32) k_dec_md5(DecBlock *db, int B, int id_rule
 
 static inline u32 cdivd(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
 
+// sq_load_model: refuse base-context tables the decoder's 8-bit cumulative form cannot hold
+cudaError_t sqk_check_seqsnap(const u8 *snap_seq, u64 nctx, int *d_flag, int *bad, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_check_seqsnap<<<256, 256, 0, st>>>((const u32 *)snap_seq, nctx, d_flag);
+    e = cudaMemcpyAsync(bad, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+
 cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
     int B = w.B;
     if (B == 0) return cudaSuccess;
     // per-block model reset (or snapshot restore) into the decoder's warp-model tables
-    k_init_wm<95, 3><<<dim3(w.nsm * 2, B), 256, 0, st>>>(w.db, 0, w.nqual, 0, w.snap_qual, 293);
-    k_init_seqtab<<<dim3(w.nsm, B), 256, 0, st>>>(w.db, (u64)w.nseq * 4, w.snap_seq);
+    k_init_q4<95><<<dim3(w.nsm * 2, B), 256, 0, st>>>(w.db, w.nqual, w.snap_qual, 293);
+    k_init_seqtab<<<dim3(w.nsm, B), 256, 0, st>>>(w.db, (u64)w.nseq, w.snap_seq);
     *launches += 2;
     if (!w.id_rule) {
         // nametab: prefix | suffix | len (256 x SIMPLE_MODEL<256> each) then 8192 x SIMPLE_MODEL<128>

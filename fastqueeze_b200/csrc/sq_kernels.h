@@ -87,3 +87,4 @@ struct DecWave {
     const u8 *snap_name, *snap_seq, *snap_qual;
 };
 cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches);
+cudaError_t sqk_check_seqsnap(const u8 *snap_seq, u64 nctx, int *d_flag, int *bad, cudaStream_t st);
