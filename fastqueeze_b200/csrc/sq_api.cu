@@ -748,7 +748,7 @@ int decode_wave(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_
         u64 nr = d.nreads;
         d.seqoff = (u32 *)need(A.take(4 * (nr + 1) + 16));
         d.seqtab = (u8 *)need(A.take((u64)w.nseq * 4));
-        d.qualtab = (u32 *)need(A.take((u64)w.nqual * SQ_WQ_STRIDE * 4));
+        d.qualtab = (u32 *)need(A.take(((u64)w.nqual + 1) * SQ_WQ_STRIDE * 4));     // + one spare slot (sq_decode.cu: QPend)
         if (!c->p.id_rule) d.nametab = (u32 *)need(A.take(SQ_WNAME_WORDS * 4));
         d.d_tip = (u8 *)need(A.take(nr + 16));
         d.d_maxq = (u8 *)need(A.take(nr + 16));
@@ -800,7 +800,7 @@ int decode_wave(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_
 u64 dec_block_cost(const sq_ctx *c, u64 reclen, const sq_block_dec &o, u32 nreads, bool host) {
     u64 t = sizeof(DecBlock) + 20 * 256;
     if (host) t += reclen + o.idcap + 2 * o.seqcap + 6ull * o.readcap;
-    t += 4ull * (nreads + 1) + (u64)c->nseq() * 4 + (u64)c->nqual() * SQ_WQ_STRIDE * 4;
+    t += 4ull * (nreads + 1) + (u64)c->nseq() * 4 + ((u64)c->nqual() + 1) * SQ_WQ_STRIDE * 4;
     if (!c->p.id_rule) t += SQ_WNAME_WORDS * 4;
     t += 6ull * nreads + 5 * o.seqcap;
     return t;

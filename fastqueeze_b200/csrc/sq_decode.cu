@@ -299,7 +299,7 @@ struct RcWin;
 SQ_D u32 recip32(u32 d) { return 0xffffffffu / (d ? d : 1u); }     // in [2^32/d - 1, 2^32/d]: mulhi(n, .) is floor(n/d) or one less
 
 template <int N>
-__global__ void __launch_bounds__(256) k_init_q4(DecBlock *db, u32 nmodels, const u8 *snap, u32 snapstride) {
+__global__ void __launch_bounds__(256) k_init_q4(DecBlock *db, u32 nmodels, const u8 *snap, u32 snapstride, u32 nsnap) {
     static_assert(N <= 96, "three entries per lane");
     int b = blockIdx.y;
     if (db[b].status != 0) return;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) k_init_q4(DecBlock *db, u32 nmodels, cons
     int lane = threadIdx.x & 31;
     u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (u32 m = warp; m < nmodels; m += nwarps) {
-        const u8 *s = snap ? snap + (u64)m * snapstride : nullptr;
+        const u8 *s = (snap && m < nsnap) ? snap + (u64)m * snapstride : nullptr;
         u32 tot = N, bub = 0;
         if (s) { tot = get_u32le(s) & 0xffffu; bub = get_u32le(s + 4) & 15u; }
         u32 f[3], sy[3], T = 0;
@@ -339,6 +339,13 @@ struct RcWin {
     const u32 *wp, *wend;    // next aligned word to fetch / first word past the stream
     u32 nxt;                 // the word fetched ahead
     SQ_D void fetch() { nxt = wp < wend ? __ldg(wp) : 0u; wp++; }
+    // the same under a predicate, without a branch (keeps the pipelined loop body one basic block)
+    SQ_D void fetch_if(bool c) {
+        u32 ok = (c && wp < wend) ? 1u : 0u, v = nxt;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(wp), "r"(ok));
+        nxt = c ? (ok ? v : 0u) : nxt;
+        wp += c ? 1 : 0;
+    }
     SQ_D void refill() {     // needs avail <= 4
         win |= (u64)__byte_perm(nxt, 0, 0x0123) << (32 - 8 * avail);
         avail += 4;
@@ -389,6 +396,37 @@ struct RcWin {
         range <<= sh;
         low <<= sh;
         if (avail <= 4) refill();
+    }
+    // The same step without a branch, for the software-pipelined quality loop: returns true when the exact
+    // loop has to run instead (carry-less adjustment possible, or more than two bytes) -- the state is then
+    // left un-renormalised for renorm_exact().
+    SQ_D bool decode_fast(u32 cum, u32 freq) {
+        u32 t = cum * range;
+        low += t;
+        code -= t;
+        range *= freq;
+        const bool slow = range < (1u << 24) && ((~(u32)(low >> 32) & 0xffffu) == 0 || range < (1u << 8));
+        u32 sh = (range < (1u << 24) ? 8u : 0u) + (range < (1u << 16) ? 8u : 0u);
+        sh = slow ? 0u : sh;
+        code = __funnelshift_l((u32)(win >> 32), code, sh);
+        win <<= sh;
+        range <<= sh;
+        low <<= sh;
+        avail -= (int)(sh >> 3);
+        const bool rf = avail <= 4;
+        const u64 add = (u64)__byte_perm(nxt, 0, 0x0123) << ((32 - 8 * avail) & 63);
+        win |= rf ? add : 0ull;
+        avail += rf ? 4 : 0;
+        fetch_if(rf);
+        return slow;
+    }
+    SQ_D void renorm_exact() {
+        for (int guard = 0; guard < 16 && range < (1u << 24); guard++) {
+            if ((low ^ (low + range)) >> 56) range = (((u32)low) | 0xffffffu) - (u32)low;
+            code = (code << 8) | get();
+            range <<= 8;
+            low <<= 8;
+        }
     }
 };
 
@@ -510,6 +548,99 @@ SQ_D u32 q4_step(uint4 &M, u32 &last, RcWin &rc, uint4 *tab, u8 *qout, int i, in
     return qq;
 }
 
+// Software-pipelined form of the same step.  A warp issues in order and at best one instruction every other
+// cycle, so what a symbol costs is (a) its instruction COUNT and (b) how well independent chains interleave.
+// The common-case update of model i (none of it on the symbol chain) is therefore DEFERRED: it is carried as a
+// pending record into the next step and sits in the same basic block as that step's search.  Cases the deferred
+// form cannot take are completed on the spot (uniform branch at the end of the step): the next symbol uses the
+// same context, the update halves or runs the 16-symbol bubble check, or the total is too small for the one-step
+// Newton refresh of the reciprocal.
+//   * the +8 masks come straight from the search predicates: lanes above the symbol's lane compare "code < c1 r"
+//     (add to all three sums), lanes below compare "code >= c3 r" (add nothing), the symbol's lane picks by p1 / p2;
+//   * reciprocal of tot + 8 from the reciprocal of tot: e1 = e - mulhi(e, e (tot + 8) - 2^32) is ceil(E (1 - d^2)),
+//     d <= 8 / tot, i.e. floor(E) or ceil(E) once 2^38 / tot^3 < 1: one downward fix-up (SQ_Q_NEWTON_MIN).
+struct QPend { uint4 M; u32 ctx, addx, addy; };
+#define SQ_Q_NEWTON_MIN 8192u
+
+SQ_D void q4_pend_none(QPend &P, u32 dummy_ctx) { P.M = make_uint4(0, 0x20000000u, 0x20000u, 0); P.ctx = dummy_ctx; P.addx = 0; P.addy = 0; }
+
+SQ_D void q4_apply(uint4 *tab, const QPend &P) {
+    uint4 Q = P.M;
+    Q.x += P.addx;
+    Q.y += P.addy;
+    Q.w += 1u << 24;                                  // the bubble count does not wrap here (checked when deferring)
+    const u32 d = Q.y >> 16;
+    u32 e = Q.z;
+    e -= __umulhi(e, e * d);                          // e * d - 2^32 fits 32 bits: the old reciprocal overshoots the new total
+    if ((i32)(e * d) >= 0) e--;                       // e * d wrapped past 2^32 - 1
+    Q.z = e;
+    q4_st(tab + (u64)P.ctx * 32, Q);
+}
+
+template <int QLEVEL, bool SAT>
+SQ_D u32 q4_pstep(uint4 &M, u32 &last, QPend &P, RcWin &rc, uint4 *tab, u8 *qp, bool more, int i, u32 &q1, u32 &q2, u32 &delta,
+                  int lane, u32 dummy_ctx) {
+    const u32 tot = M.y >> 16;
+    const u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
+    u32 c0 = __shfl_up_sync(FULL, c3, 1);
+    c0 = lane ? c0 : 0u;
+    q4_apply(tab, P);                                 // previous symbol's model (or the dummy slot): interleaves with the search below
+    u32 r = __umulhi(rc.range, M.z);
+    r += (rc.range - r * tot >= tot) ? 1u : 0u;
+    const u32 code = rc.code;
+    const bool p1 = code >= c1 * r, p2 = code >= c2 * r, p3 = code >= c3 * r;   // monotone
+    const u32 miss = __ballot_sync(FULL, p3);
+    const int kl = __popc(miss);                      // hits are monotone in the lane index
+    const u32 cex = p2 ? c2 : (p1 ? c1 : c0);
+    const u32 cnx = p2 ? c3 : (p1 ? c2 : c1);
+    u32 A = ((cnx - cex) << 16) + cex;
+    const u32 sy = __byte_perm(M.w, 0, 0x4440u + (p1 ? 1u : 0u) + (p2 ? 1u : 0u));
+    const u32 qq = __shfl_sync(FULL, sy, kl);
+    A = __shfl_sync(FULL, A, kl);
+    const u32 addx = p2 ? (p3 ? 0u : 0u) : (p1 ? 0x00080000u : 0x00080008u);
+    const u32 addy = p3 ? 0x00080000u : 0x00080008u;
+    const u32 amax = q1 > q2 ? q1 : q2;
+    u32 K = 0;
+    if (QLEVEL > 1) K |= (u32)(q1 == q2) << 12;
+    if (QLEVEL > 2) K |= (i <= 111) ? (u32)((i + 15) & 0x78) << 13 : 0xf0000u;
+    u32 nl;
+    if (SAT || QLEVEL == 1) {
+        if (QLEVEL > 1) K |= (56u & 0xf8u) << 10;
+        const u32 mk = more ? 0xfffu : 0u;
+        K = more ? K : 0u;
+        nl = ((amax * 64 + qq) & mk) | K;
+    } else {
+        int dd = (int)q1 - (int)qq;
+        u32 d2 = delta + (u32)(dd > 0 ? dd : 0);
+        nl = (((amax * 64 + qq) & 0xfffu) | K | (((d2 < 56 ? d2 : 56u) & 0xf8u) << 10)) & (more ? 0xffffffffu : 0u);
+        delta = d2;
+    }
+    const uint4 Mn = q4_ld(tab + (u64)nl * 32);
+    rc.range = r;
+    rc.decode(A & 0xffffu, A >> 16);
+    if (lane == 0) *qp = (u8)(qq + 33);
+    // deferred unless: same context next, halving (tot + 8 > 0xffe0), total below the Newton range, bubble check due
+    const bool special = (M.y - (SQ_Q_NEWTON_MIN << 16)) > (((0xffe0u - 8u - SQ_Q_NEWTON_MIN) << 16) | 0xffffu);
+    const bool bubdue = ((M.w + (1u << 24)) & (15u << 24)) == 0;
+    if (nl == last || special || bubdue) {
+        M.x += addx;
+        M.y += addy;
+        M.w = (M.w & 0xf0ffffffu) | ((M.w + (1u << 24)) & (15u << 24));
+        if (tot + 8 > 0xffe0u) q4_halve(M, lane);
+        if (bubdue) q4_bubble(M, kl, (p1 ? 1 : 0) + (p2 ? 1 : 0), lane);
+        M.z = recip32(M.y >> 16);
+        q4_st(tab + (u64)last * 32, M);
+        if (nl != last) M = Mn;
+        q4_pend_none(P, dummy_ctx);
+    } else {
+        P.M = M; P.ctx = last; P.addx = addx; P.addy = addy;
+        M = Mn;
+    }
+    last = nl;
+    q2 = q1; q1 = qq;
+    return qq;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Len stream (decompressLen_short @0x428170 / decode_len_short @0x427ca0) + read offsets.
 // The reference keeps last_len across blocks per decoder instance; a zero-length
@@ -616,6 +747,7 @@ struct SeqPipe {
     SQ_D void init() { step = 0; lc0 = lc1 = lc2 = lc3 = 0xffffffffu; lv0 = lv1 = lv2 = lv3 = 0; }
 };
 
+SQ_D u32 base_halve(u32 x);
 __global__ void k_init_seqtab(DecBlock *db, u64 nctx, const u8 *snap) {
     int b = blockIdx.y;
     if (db[b].status != 0) return;
@@ -625,7 +757,8 @@ __global__ void k_init_seqtab(DecBlock *db, u64 nctx, const u8 *snap) {
         u32 v = s ? s[i] : 0x03030303u;
         u32 s0 = v & 0xff, s1 = (v >> 8) & 0xff, s2 = (v >> 16) & 0xff, s3 = v >> 24;
         u32 c1 = s0, c2 = c1 + s1, c3 = c2 + s2, tot = c3 + s3;     // <= 254 for every snapshot sq_load_model accepts
-        t[i] = (c1 & 0xff) | ((c2 & 0xff) << 8) | ((c3 & 0xff) << 16) | ((tot & 0xff) << 24);
+        u32 w = (c1 & 0xff) | ((c2 & 0xff) << 8) | ((c3 & 0xff) << 16) | ((tot & 0xff) << 24);
+        t[i] = (w >> 24) > 253 ? base_halve(w) : w;
     }
 }
 // a snapshot whose base contexts sum above 254 cannot come from the reference's training (same update rule)
@@ -634,6 +767,18 @@ __global__ void k_check_seqsnap(const u32 *snap, u64 nctx, int *bad) {
         u32 v = snap[i];
         if ((v & 0xff) + ((v >> 8) & 0xff) + ((v >> 16) & 0xff) + (v >> 24) > 254u) *bad = 1;
     }
+}
+
+// The reference halves a context whose total has passed 253 when it next CODES with it (@0x421fb0).  Nothing
+// else reads the context in between, so the decoder halves when it WRITES the word (and when it builds the
+// table): the test leaves the symbol chain.  S -= S >> 1 on the four counters behind the cumulative bytes.
+SQ_D u32 base_halve(u32 x) {
+    u32 tot = x >> 24;
+    u32 s0 = x & 0xff, s1 = ((x >> 8) - x) & 0xff, s2 = ((x >> 16) - (x >> 8)) & 0xff, s3 = (tot - (x >> 16)) & 0xff;
+    s0 -= s0 >> 1; s1 -= s1 >> 1; s2 -= s2 >> 1; s3 -= s3 >> 1;
+    u32 c2 = s0 + s1, c3 = c2 + s2;
+    tot = (c3 + s3) & 0xff;
+    return s0 | ((c2 & 0xff) << 8) | ((c3 & 0xff) << 16) | (tot << 24);
 }
 
 SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcWin &rc, u32 &last, u32 mask, u32 nb, SeqPipe &P, int lane, u64 pol) {
@@ -657,14 +802,7 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcWin &rc, u32 &las
     const bool h0 = P.lc0 == last, h1 = P.lc1 == last, h2 = P.lc2 == last, h3 = P.lc3 == last;
     const u32 fv = h0 ? P.lv0 : (h1 ? P.lv1 : (h2 ? P.lv2 : P.lv3));
     x = (h0 || h1 || h2 || h3) ? fv : x;
-    u32 tot = x >> 24;
-    if (tot > 253) {                                 // rare: halve the four counters (S -= S >> 1)
-        u32 s0 = x & 0xff, s1 = ((x >> 8) - x) & 0xff, s2 = ((x >> 16) - (x >> 8)) & 0xff, s3 = (tot - (x >> 16)) & 0xff;
-        s0 -= s0 >> 1; s1 -= s1 >> 1; s2 -= s2 >> 1; s3 -= s3 >> 1;
-        u32 c2 = s0 + s1, c3 = c2 + s2;
-        tot = (c3 + s3) & 0xff;
-        x = s0 | ((c2 & 0xff) << 8) | ((c3 & 0xff) << 16) | (tot << 24);
-    }
+    const u32 tot = x >> 24;                         // <= 253: contexts are halved when they are written (base_halve)
     u32 r = __umulhi(rc.range, rlut[tot]);
     u32 rem = rc.range - r * tot;
     r += (rem >= tot) ? 1u : 0u;
@@ -675,9 +813,48 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcWin &rc, u32 &las
     const u32 cum = ((x << 8) >> sh) & 0xff, cnx = (x >> sh) & 0xff;
     rc.range = r;
     rc.decode(cum, (cnx - cum) & 0xff);
-    const u32 nv = x + (0x01010101u << sh);          // S[b]++: every cumulative byte at or above b
+    u32 nv = x + (0x01010101u << sh);                // S[b]++: every cumulative byte at or above b
+    if ((nv >> 24) > 253) nv = base_halve(nv);
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(S4), "r"(nv), "l"(pol) : "memory");
     __syncwarp();
+    P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
+    P.step++;
+    last = (last * 4 + b) & mask;
+    return b;
+}
+
+// The same step for the bulk of a read (its first SQ_LOOK bases go through decode_base, which reads the table
+// directly): no look-ahead test, no cache-policy operands (they cost more instructions than they save), bytes picked
+// with PRMT.  A warp issues at best one instruction every other cycle, so the count is what matters here.
+SQ_D u32 lds32(u32 saddr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
+// ring_s / rlut_s: shared-window addresses of the ring and the reciprocal table (computed once per warp);
+// cp_src: seqtab + lane * 16, cp_dst: ring_s + lane * 16 (lanes below SQ_LOOK_N / 4 copy)
+SQ_D u32 base_step_fast(u8 *seqtab, const u8 *cp_src, u32 cp_dst, u32 ring_s, u32 rlut_s, RcWin &rc, u32 &last, u32 mask, SeqPipe &P, int lane) {
+    if (lane < SQ_LOOK_N / 4) {
+        const u32 basec = (last << (2 * SQ_LOOK)) & mask;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(cp_dst + (((P.step + SQ_LOOK) & 7) * SQ_LOOK_N * 4)), "l"(cp_src + ((u64)basec << 2)) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(SQ_LOOK) : "memory");
+    __syncwarp();
+    u32 x = lds32(ring_s + ((P.step & 7) * SQ_LOOK_N + (last & (SQ_LOOK_N - 1))) * 4);
+    const bool h0 = P.lc0 == last, h1 = P.lc1 == last, h2 = P.lc2 == last, h3 = P.lc3 == last;
+    const u32 fv = h0 ? P.lv0 : (h1 ? P.lv1 : (h2 ? P.lv2 : P.lv3));
+    x = (h0 || h1 || h2 || h3) ? fv : x;
+    const u32 tot = x >> 24;
+    u32 r = __umulhi(rc.range, lds32(rlut_s + tot * 4));
+    r += (rc.range - r * tot >= tot) ? 1u : 0u;
+    const u32 code = rc.code;
+    const u32 c1 = __byte_perm(x, 0, 0x4440), c2 = __byte_perm(x, 0, 0x4441), c3 = __byte_perm(x, 0, 0x4442);
+    const bool p1 = code >= c1 * r, p2 = code >= c2 * r, p3 = code >= c3 * r;
+    const u32 b = (p1 ? 1u : 0u) + (p2 ? 1u : 0u) + (p3 ? 1u : 0u);
+    const u32 cum = p3 ? c3 : (p2 ? c2 : (p1 ? c1 : 0u));
+    const u32 cnx = p3 ? tot : (p2 ? c3 : (p1 ? c2 : c1));
+    rc.range = r;
+    rc.decode(cum, cnx - cum);
+    u32 nv = x + (0x01010101u << (8 * b));
+    if ((nv >> 24) > 253) nv = base_halve(nv);
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(seqtab + (u64)last * 4), "r"(nv) : "memory");
     P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
     P.step++;
     last = (last * 4 + b) & mask;
@@ -819,7 +996,7 @@ SQ_D void md5_chase(DecBlock &d, volatile u32 *qprog, volatile u32 *sprog, const
 }
 
 template <int QLEVEL>
-__global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 seqmask, int inline_md5) {
+__global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 seqmask, int inline_md5, u32 qdummy) {
     constexpr int qlevel = QLEVEL;
     __shared__ __align__(16) MainSmem sm;
     DecBlock &d = db[blockIdx.x];
@@ -868,18 +1045,28 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         rc.start(rec + d.off[7], rec + d.off[7] + d.len[7]);
         uint4 *tab = (uint4 *)d.qualtab + lane;
         u8 *qual = d.qual;
+        const u32 dummy_ctx = qdummy;                          // spare model slot behind the table: target of "no pending update"
         u32 last = 0;
         uint4 M = q4_ld(tab);                                  // context 0 opens every read
+        QPend P;
+        q4_pend_none(P, dummy_ctx);
+        u32 off_n = nreads ? seqoff[0] : 0;
+        int len_n = nreads ? seqlen[0] : 0;
         for (u32 r = 0; r < nreads; r++) {
-            u8 *q = qual + seqoff[r];
-            const int len = seqlen[r];
+            u8 *q = qual + off_n;
+            const int len = len_n;
+            if (r + 1 < nreads) { off_n = seqoff[r + 1]; len_n = seqlen[r + 1]; }     // fetched a read ahead
             u32 delta = 5, q1 = 0, q2 = 0, qq = 0;
             int i = 0;
             if (qlevel > 1)
-                for (; i < len && delta < 56 && qq != 94; i++) qq = q4_step<QLEVEL, false>(M, last, rc, tab, q, i, len, q1, q2, delta, lane);
-            for (; i < len && qq != 94; i++) qq = q4_step<QLEVEL, true>(M, last, rc, tab, q, i, len, q1, q2, delta, lane);
+                for (; i < len && delta < 56 && qq != 94; i++)
+                    qq = q4_pstep<QLEVEL, false>(M, last, P, rc, tab, q + i, i + 1 < len, i, q1, q2, delta, lane, dummy_ctx);
+            for (; i < len && qq != 94; i++)
+                qq = q4_pstep<QLEVEL, true>(M, last, P, rc, tab, q + i, i + 1 < len, i, q1, q2, delta, lane, dummy_ctx);
             if (qq == 94) {                                    // the rest of the read is '#' (@0x42a9a0); context 0 opens the next read
                 for (int t = i - 1 + lane; t < len; t += 32) q[t] = '#';
+                q4_apply(tab, P);
+                q4_pend_none(P, dummy_ctx);
                 if (last != 0) { M = q4_ld(tab); last = 0; }
             }
             if ((r & 15) == 15 || r + 1 == nreads) {
@@ -925,6 +1112,9 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         rc.start(rec + d.off[6], rec + d.off[6] + d.len[6]);
         SeqPipe P;
         P.init();
+        const u32 ring_s = (u32)__cvta_generic_to_shared(sm.ring), rlut_s = (u32)__cvta_generic_to_shared(sm.rlut);
+        const u8 *cp_src = seqtab + lane * 16;
+        const u32 cp_dst = ring_s + lane * 16;
         u32 i_mq = 0, i_ch = 0, i_pos = 0;
         for (u32 r = 0; r < nreads; r++) {
             if (inline_md5 && r && (r & 15) == 0) {             // reads [0, r) are final: let the MD5 chaser have them
@@ -937,8 +1127,13 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
             u32 nb = 0;
             bool flagged = r < n_tip && __ldcg(d_tip + r);
             if (!flagged) {
-                for (int i = 0; i < len; i++) {
+                int i = 0;
+                for (; i < len && i < SQ_LOOK; i++) {
                     u32 bb = decode_base(seqtab, sm.ring, sm.rlut, rc, last, seqmask, nb++, P, lane, pol);
+                    if (lane == 0) seq[i] = base_char(bb);
+                }
+                for (; i < len; i++) {
+                    u32 bb = base_step_fast(seqtab, cp_src, cp_dst, ring_s, rlut_s, rc, last, seqmask, P, lane);
                     if (lane == 0) seq[i] = base_char(bb);
                 }
                 continue;
@@ -1016,7 +1211,7 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
     int B = w.B;
     if (B == 0) return cudaSuccess;
     // per-block model reset (or snapshot restore) into the decoder's warp-model tables
-    k_init_q4<95><<<dim3(w.nsm * 2, B), 256, 0, st>>>(w.db, w.nqual, w.snap_qual, 293);
+    k_init_q4<95><<<dim3(w.nsm * 2, B), 256, 0, st>>>(w.db, w.nqual + 1, w.snap_qual, 293, w.nqual);      // + the spare slot (QPend)
     k_init_seqtab<<<dim3(w.nsm, B), 256, 0, st>>>(w.db, (u64)w.nseq, w.snap_seq);
     *launches += 2;
     if (!w.id_rule) {
@@ -1050,9 +1245,9 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
     static int inl = -1;
     if (inl < 0) { const char *e = getenv("SQ_DEC_INLINE_MD5"); inl = e ? atoi(e) != 0 : 1; }
     const int inline_md5 = (w.md5 && inl) ? 1 : 0;
-    if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5);
-    else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5);
-    else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5);
+    if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
+    else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
+    else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
     *launches += 2;
     if (w.md5 && !inline_md5) { k_dec_md5<<<cdivd(3ull * B, 32), 32, 0, st>>>(w.db, B, w.id_rule); *launches += 1; }
     return cudaGetLastError();

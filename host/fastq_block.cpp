@@ -91,7 +91,7 @@ bool BlockReader::next_text(std::vector<char> &t1, std::vector<char> &t2) {
     const int nf = pe_ ? 2 : 1;
     uint64_t quota = pe_ ? block_bytes_ / 2 : block_bytes_;            // @0x432dd2: shr $1 for PE
     std::vector<char> *t[2] = {&t1, &t2};
-    bool shortread = false;
+    bool shortread[2] = {false, false};
     for (int k = 0; k < nf; k++) {
         std::vector<char> &b = *t[k];
         size_t L = left_[k].size();
@@ -101,14 +101,16 @@ bool BlockReader::next_text(std::vector<char> &t1, std::vector<char> &t2) {
         size_t want = quota > L ? quota - L : 0;
         size_t got = want ? f_[k].read(b.data() + L, want) : 0;
         if (first_[k].empty()) first_line(b.data() + L, got, first_[k]);
-        if (got < want) shortread = true;
+        if (got < want) shortread[k] = true;
         b.resize(L + got);
     }
-    if (shortread) {                      // end of input: the rest goes out as the last block
-        eof_ = true;
-        if (pe_) {                        // cultPEbuf(.., false): both files keep min(#lines) lines -- equal for valid PE
-        }
-        return !t1.empty();
+    // doReadJob @0x432a80 ends on a short read; doReadPEJob ends only when BOTH files came up short in the same
+    // round (@0x432ec2-0x432ede: got[0] >= want[0] || got[1] >= want[1] keeps cutting).  Mates of unequal byte
+    // size (trimmed reads, R1 / R2 of different length) exhaust one file first: its leftover keeps feeding blocks
+    // whose size the other file's line count decides.
+    if (pe_ ? (shortread[0] && shortread[1]) : shortread[0]) {
+        eof_ = true;                      // the rest goes out as the last block: cultPEbuf(.., false) keeps
+        return !t1.empty();               // min(#lines) lines of both buffers -- equal for valid paired input
     }
     if (!pe_) {                           // cultbuf @0x432530
         int total = (int)t1.size();

@@ -68,6 +68,9 @@ CASES = [
          config={"Slevel": 0}),
     dict(name="illumina_pe150_s5", src=dict(kind="illumina_pe150", n_templates=700, seed=24, n_rate=0.001), pe=True, opts=[],
          config={"Slevel": 5}),
+    # mate files of unequal size (trimmed reads): one file runs dry first, doReadPEJob keeps cutting until both do
+    dict(name="illumina_pe_trim_blocks", src=dict(kind="illumina_pe_trim", n_templates=7000, seed=51), pe=True, opts=[],
+         config={"BlockSize(M)": 1}),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]

@@ -99,6 +99,12 @@ def make_block(kind="illumina_pe150", n_templates=1000, seed=7, first=0, n_rate=
         return dict(ids=np.frombuffer(b"".join(idl), dtype=np.uint8).copy(), idlen=np.array([len(x) for x in idl], np.uint16),
                     seq=BASES[rng.integers(0, 4, tot)], qual=(np.clip(np.rint(rng.normal(20, 6, tot)), 2, 40).astype(np.uint8) + 33),
                     seqlen=np.array(lens, np.int32), pe=False)
+    if kind == "illumina_pe_trim":  # adapter-trimmed pairs: every read keeps a random prefix, mate 2 shorter on average,
+        full = make_block("illumina_pe150", n_templates, seed, first, n_rate, hash_tail)   # so the mate files differ in size
+        n = full["seqlen"].shape[0]
+        keep = np.where(np.arange(n) % 2 == 0, rng.integers(100, 151, n), rng.integers(40, 151, n)).astype(np.int32)
+        m = (np.arange(150)[None, :] < keep[:, None]).reshape(-1)
+        return dict(ids=full["ids"], idlen=full["idlen"], seq=full["seq"][m].copy(), qual=full["qual"][m].copy(), seqlen=keep, pe=True)
     pe = kind not in ("se100_q8", "sra_len_se100")
     L = 150 if kind == "illumina_pe150" else 100
     n = n_templates * (2 if pe else 1)
