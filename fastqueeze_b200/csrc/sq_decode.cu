@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
             }
         }
         SQ_TICK("qual");
-    } else {                                                   // Dege streams, then bases (decompressSeq @0x42e390)
+    } else if (wid == 2) {                                     // Dege streams, then bases (decompressSeq @0x42e390)
         if (lane == 0) {
             u32 n_tip = dec_small<2>(d, 23, sm.tip, d.d_tip, d.nreads, 0);
             u32 n_ch = dec_small<11>(d, 14, sm.ch, d.d_ch, (u32)d.seqbytes, 1);
@@ -1114,6 +1114,8 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
         P.init();
         const u32 ring_s = (u32)__cvta_generic_to_shared(sm.ring), rlut_s = (u32)__cvta_generic_to_shared(sm.rlut);
         const u8 *cp_src = seqtab + lane * 16;
+        u32 smask = seqmask;
+        asm volatile("mov.u32 %0, %0;" : "+r"(smask));           // keep the mask in a register (else it is re-read from the parameter bank every base)
         const u32 cp_dst = ring_s + lane * 16;
         u32 i_mq = 0, i_ch = 0, i_pos = 0;
         for (u32 r = 0; r < nreads; r++) {
@@ -1133,7 +1135,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
                     if (lane == 0) seq[i] = base_char(bb);
                 }
                 for (; i < len; i++) {
-                    u32 bb = base_step_fast(seqtab, cp_src, cp_dst, ring_s, rlut_s, rc, last, seqmask, P, lane);
+                    u32 bb = base_step_fast(seqtab, cp_src, cp_dst, ring_s, rlut_s, rc, last, smask, P, lane);
                     if (lane == 0) seq[i] = base_char(bb);
                 }
                 continue;
