@@ -346,7 +346,6 @@ def main():
         launches[0] += int(L_.sq_last_launches(h))
 
     split_ms = {"enc": [], "dec": []}
-    enc_subwaves = [0]
 
     def step_device(record=False):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
@@ -355,7 +354,6 @@ def main():
         r = L_.sq_encode_blocks_dev(h, ins, nblocks, outs)
         if r:
             raise SystemExit("encode failed: %d %s" % (r, L_.sq_last_error(h)))
-        enc_subwaves[0] = int(L_.sq_last_subwaves(h))
         if record:
             ev[1].record(stream)
             timings("enc.")
@@ -503,7 +501,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "fastq_MB_per_gpu": round(fastq_bytes / 1e6, 1), "blocks_per_gpu": nblocks,
                        "ratio": round(fastq_bytes / arc_bytes, 3), "usemodel": usemodel, "l2": "inputs larger than L2 (>= 52 MB per block stream set; no flush)",
-                       "wave_blocks": int(L_.sq_last_wave_blocks(h)), "encode_subwaves": enc_subwaves[0]},
+                       "wave_blocks": int(L_.sq_last_wave_blocks(h))},
             "compress_MBps": round(world * fastq_bytes / 1e6 / (enc_ms / 1e3), 2) if enc_ms else None,
             "decompress_MBps": round(world * fastq_bytes / 1e6 / (dec_ms / 1e3), 2) if dec_ms else None,
             "stage_ms": {k: round(v, 3) for k, v in sorted(mean_ms.items(), key=lambda kv: -kv[1])},

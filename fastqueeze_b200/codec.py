@@ -59,7 +59,6 @@ class DebugInfo:
     stages: dict = field(default_factory=dict)
     launches: int = 0
     wave_blocks: int = 0
-    subwaves: int = 0
 
 
 def _c(a, dt):
@@ -142,7 +141,6 @@ class EncapFqzComp:
         dbg.stages = {names[i].decode(): float(ms[i]) for i in range(n)}
         dbg.launches = int(self._L.sq_last_launches(self._h))
         dbg.wave_blocks = int(self._L.sq_last_wave_blocks(self._h))
-        dbg.subwaves = int(self._L.sq_last_subwaves(self._h))
 
     # doFqzEncode @0x42d2d0 over a batch of blocks; fills membuf.out, returns the record lengths
     def doFqzEncode(self, membufs, dbg: DebugInfo = None, raise_on_error=True):

@@ -6,7 +6,6 @@
 #include "sq_kernels.h"
 
 #include <algorithm>
-#include <functional>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -72,7 +71,6 @@ struct sq_ctx {
     StageTimer timer;
     u64 launches = 0;
     int last_wave_blocks = 0;
-    int last_subwaves = 0;
     // last encoded wave (debug fetch)
     EncWave last{};
     std::vector<BlockDesc> last_bd;
@@ -139,7 +137,7 @@ extern "C" int sq_create(const sq_params *p, sq_ctx **out) {
     if (want == 0) {
         size_t fr = 0, tot = 0;
         if ((e = cudaMemGetInfo(&fr, &tot)) != cudaSuccess) return fail(cudaGetErrorString(e), SQ_ERR_CUDA);
-        want = (u64)(fr * 0.88);
+        want = (u64)(fr * 0.8);
     }
     if ((e = cudaMalloc((void **)&c->arena.base, want)) != cudaSuccess)
         return fail(std::string("workspace cudaMalloc: ") + cudaGetErrorString(e), SQ_ERR_NOMEM);
@@ -199,7 +197,6 @@ extern "C" int sq_last_timings(const sq_ctx *c, const char **names, float *ms, i
 }
 extern "C" uint64_t sq_last_launches(const sq_ctx *c) { return c ? c->launches : 0; }
 extern "C" int sq_last_wave_blocks(const sq_ctx *c) { return c ? c->last_wave_blocks : 0; }
-extern "C" int sq_last_subwaves(const sq_ctx *c) { return c ? c->last_subwaves : 0; }
 
 // ---------------------------------------------------------------------------------------------
 // encode
@@ -227,25 +224,39 @@ BlkCost block_cost(const sq_ctx *c, const sq_block_in &b, bool host) {
     return k;
 }
 
-// Workspace accounting of one encode call.  PERSISTENT data lives until the records are packed (inputs, per-read
-// arrays, the coding triples of every stream, side streams, records); TRANSIENT data belongs to the context / sort /
-// replay front end and is reused by every sub-wave (element double buffer, radix histograms, segment list).  The
-// front end may run over a block range at a time; the serial range-coder passes run ONCE over all blocks after it
-// (their time is per-chain latency, whatever the number of chains: DESIGN.md section 5), and their worst-case output
-// scratch takes the place of the front-end buffers, which are dead by then.
-u64 block_transient(const sq_ctx *c, const BlkCost &k) {
-    u64 nctx[ST_COUNT] = {c->nseq(), c->nqual(), NCTX_NAME};
-    u64 me = 0, ms = 0;
-    for (int s = 0; s < ST_COUNT; s++) { me = std::max(me, k.eb[s]); ms = std::max(ms, std::min<u64>(k.eb[s], nctx[s])); }
-    u64 tiles = (me + SQ_TILE - 1) / SQ_TILE;
-    return 16 * (me + 1) + 8 * (ms + 1) + (u64)(1u << SQ_SORT_BITS_WIDE) * (tiles + 1) * 4 + 4096;
-}
-u64 block_persistent(const BlkCost &k) {
-    u64 t = k.inputs + k.perread + k.side + k.rec + sizeof(BlockDesc) + sizeof(BlockState) + 6 * 4 + 8 + 4 + 8 + 1024;
-    for (int s = 0; s < ST_COUNT; s++) t += (s == ST_SEQ ? 4 : 8) * (k.eb[s] + 2) + 256;
-    return t;
-}
-#define SQ_MIN_SUBWAVE 8          /* a job is only accepted if at least this many blocks of front end fit beside it */
+struct WaveAcc {
+    u64 lin = 0;                  // linear part
+    u64 sumeb[ST_COUNT] = {0, 0, 0};
+    u64 maxeb[ST_COUNT] = {0, 0, 0};
+    u64 segsum[ST_COUNT] = {0, 0, 0};
+    int B = 0;
+    u64 total(const sq_ctx *c) const {
+        u64 t = lin + 64 * 1024;
+        u64 me = 0, ms = 0, mt = 0;
+        for (int s = 0; s < ST_COUNT; s++) {
+            t += (s == ST_SEQ ? 4 : 8) * sumeb[s] + 256;
+            me = std::max(me, sumeb[s]);
+            ms = std::max(ms, segsum[s]);
+            mt = std::max(mt, (maxeb[s] + SQ_TILE - 1) / SQ_TILE);
+        }
+        t += 16 * me + 512;                                   // elemA + elemB
+        t += 8 * ms + 256;                                    // seglist
+        t += (u64)B * (1u << SQ_SORT_BITS_WIDE) * mt * 4 + 256;    // hist
+        t += (u64)B * (sizeof(BlockDesc) + sizeof(BlockState) + 6 * 4 + 8 + 4) + 2048;
+        (void)c;
+        return t;
+    }
+    void add(const sq_ctx *c, const BlkCost &k) {
+        lin += k.inputs + k.perread + k.obuf + k.side + k.rec;
+        u64 nctx[ST_COUNT] = {c->nseq(), c->nqual(), NCTX_NAME};
+        for (int s = 0; s < ST_COUNT; s++) {
+            sumeb[s] += k.eb[s];
+            maxeb[s] = std::max(maxeb[s], k.eb[s]);
+            segsum[s] += std::min<u64>(k.eb[s], nctx[s]);
+        }
+        B++;
+    }
+};
 
 template <class T> T *take(Arena &a, u64 count) { return (T *)a.take(count * sizeof(T)); }
 
@@ -311,7 +322,18 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     w.acgtoff = (u32 *)need(take<u32>(A, Rr)); w.qlen2 = (u32 *)need(take<u32>(A, Rr));
     w.qoff = (u32 *)need(take<u32>(A, Rr)); w.noff = (u32 *)need(take<u32>(A, Rr));
     w.tip = (u8 *)need(take<u8>(A, Rr)); w.np = (u8 *)need(take<u8>(A, Rr)); w.ns = (u8 *)need(take<u8>(A, Rr));
+    u64 maxsum = std::max(sum[0], std::max(sum[1], sum[2]));
+    w.elemA = (u64 *)need(take<u64>(A, maxsum + 1));
+    w.elemB = (u64 *)need(take<u64>(A, maxsum + 1));
     for (int s = 0; s < ST_COUNT; s++) w.triples[s] = (u64 *)need(A.take((s == ST_SEQ ? 4 : 8) * (sum[s] + 2)));
+    u64 maxtiles = 0;
+    for (int s = 0; s < ST_COUNT; s++) maxtiles = std::max(maxtiles, (w.maxbound[s] + SQ_TILE - 1) / SQ_TILE);
+    w.hist = (u32 *)need(take<u32>(A, (u64)n * (1u << SQ_SORT_BITS_WIDE) * maxtiles + 1));
+    u64 segcap = std::max(segsum[0], std::max(segsum[1], segsum[2])) + 1;
+    if (segcap > 0xffffffffull) { c->err = "segment list too large"; return SQ_ERR_ARG; }
+    w.segcap = (u32)segcap;
+    w.seglist = (u64 *)need(take<u64>(A, segcap));
+    w.obuf = (u8 *)need(take<u8>(A, osum + 16));
     w.sidebuf = (u8 *)need(take<u8>(A, sidesum + 16));
     if (host) { w.recbuf = (u8 *)need(take<u8>(A, recsum + 16)); w.recbuf_cap = recsum; }
     // inputs
@@ -333,68 +355,6 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
         else d.qual_work = const_cast<u8 *>(d.qual);
     }
     if (!ok) { c->err = "internal: wave does not fit the workspace"; return SQ_ERR_NOMEM; }
-    // ---- front-end sub-waves: greedy block ranges whose transient buffers fit what is left of the arena
-    struct Sub { int b0, b1; u64 esum[ST_COUNT], emax[ST_COUNT], seg[ST_COUNT]; };
-    std::vector<Sub> subs;
-    u32 *d_rbase_sub = nullptr;
-    {
-        u64 avail = A.cap > A.used + (1u << 20) ? A.cap - A.used - (1u << 20) : 0;
-        if (osum + 4096 > avail) { c->err = "internal: range-coder scratch does not fit the workspace"; return SQ_ERR_NOMEM; }
-        auto cost = [&](const Sub &u) {
-            u64 me = 0, ms = 0, mt = 0;
-            for (int s = 0; s < ST_COUNT; s++) {
-                me = std::max(me, u.esum[s]); ms = std::max(ms, u.seg[s]);
-                mt = std::max(mt, (u.emax[s] + SQ_TILE - 1) / SQ_TILE);
-            }
-            return 16 * (me + 1) + 8 * (ms + 1) + (u64)(u.b1 - u.b0) * (1u << SQ_SORT_BITS_WIDE) * mt * 4 + 4 * ((u64)n + subs.size() + 8) + 8192;
-        };
-        Sub cur{0, 0, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        for (int i = 0; i < n; i++) {
-            Sub t = cur;
-            t.b1 = i + 1;
-            for (int s = 0; s < ST_COUNT; s++) {
-                t.esum[s] += bd[i].ebound[s]; t.emax[s] = std::max(t.emax[s], bd[i].ebound[s]);
-                t.seg[s] += std::min<u64>(bd[i].ebound[s], nctx[s]);
-            }
-            if (cost(t) > avail && cur.b1 > cur.b0) {
-                subs.push_back(cur);
-                cur = Sub{i, i + 1, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-                for (int s = 0; s < ST_COUNT; s++) { cur.esum[s] = cur.emax[s] = bd[i].ebound[s]; cur.seg[s] = std::min<u64>(bd[i].ebound[s], nctx[s]); }
-            } else cur = t;
-        }
-        subs.push_back(cur);
-        u64 me = 0, ms = 0, mh = 0;
-        for (auto &u : subs) {
-            if (cost(u) > avail) { c->err = "internal: a front-end sub-wave does not fit the workspace"; return SQ_ERR_NOMEM; }
-            u64 mt = 0;
-            for (int s = 0; s < ST_COUNT; s++) { me = std::max(me, u.esum[s]); ms = std::max(ms, u.seg[s]); mt = std::max(mt, (u.emax[s] + SQ_TILE - 1) / SQ_TILE); }
-            mh = std::max(mh, (u64)(u.b1 - u.b0) * (1u << SQ_SORT_BITS_WIDE) * mt);
-        }
-        if (ms + 1 > 0xffffffffull) { c->err = "segment list too large"; return SQ_ERR_ARG; }
-        d_rbase_sub = (u32 *)need(take<u32>(A, (u64)n + subs.size() + 1));
-        // one region: front-end buffers first, the range-coder scratch over the same bytes afterwards
-        u64 fe = 8 * (me + 1) * 2 + 4 * (mh + 1) + 8 * (ms + 1) + 4 * 256;
-        u8 *region = (u8 *)need(A.take(std::max(fe, osum + 16)));
-        if (region) {
-            u64 o = 0;
-            auto sub_take = [&](u64 bytes) { u8 *p = region + o; o = (o + bytes + 255) & ~(u64)255; return p; };
-            w.elemA = (u64 *)sub_take(8 * (me + 1));
-            w.elemB = (u64 *)sub_take(8 * (me + 1));
-            w.hist = (u32 *)sub_take(4 * (mh + 1));
-            w.seglist = (u64 *)sub_take(8 * (ms + 1));
-            w.obuf = region;
-        }
-        w.segcap = (u32)(ms + 1);
-        if (!ok) { c->err = "internal: front-end buffers do not fit the workspace"; return SQ_ERR_NOMEM; }
-    }
-    // block-range-relative read bases, one run of (blocks + 1) entries per sub-wave
-    std::vector<u32> rsub;
-    std::vector<size_t> rsub_at(subs.size());
-    for (size_t k = 0; k < subs.size(); k++) {
-        rsub_at[k] = rsub.size();
-        for (int i = subs[k].b0; i <= subs[k].b1; i++) rsub.push_back(rbase[i] - rbase[subs[k].b0]);
-    }
-    c->last_subwaves = (int)subs.size();
 
     StageTimer &T = c->timer;
     T.begin_wave();
@@ -419,7 +379,6 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
             if (bd[i].seqbytes) CUDA_OK(c, cudaMemcpyAsync(bd[i].qual_work, bd[i].qual, bd[i].seqbytes, cudaMemcpyDeviceToDevice, st));
     CUDA_OK(c, cudaMemcpyAsync(w.bd, bd.data(), sizeof(BlockDesc) * n, cudaMemcpyHostToDevice, st));
     CUDA_OK(c, cudaMemcpyAsync(w.rbase, rbase.data(), 4 * (n + 1), cudaMemcpyHostToDevice, st));
-    CUDA_OK(c, cudaMemcpyAsync(d_rbase_sub, rsub.data(), 4 * rsub.size(), cudaMemcpyHostToDevice, st));
     CUDA_OK(c, cudaMemsetAsync(w.bs, 0, sizeof(BlockState) * n, st));
     T.close(sp, st);
 
@@ -428,39 +387,37 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     // context / sort / replay kernels of the main stream and are joined before the pack.
     u64 *L = &c->launches;
     cudaStream_t s_md5 = c->aux[0], s_side = c->aux[1];
+    CUDA_OK(c, cudaEventRecord(c->ev[0], st));                       // inputs resident
+    CUDA_OK(c, cudaStreamWaitEvent(s_md5, c->ev[0], 0));
+    sp = T.open("md5", s_md5);
+    CUDA_OK(c, sqk_md5(w, s_md5, L));
+    T.close(sp, s_md5);
+    CUDA_OK(c, cudaEventRecord(c->ev[1], s_md5));
+
     sp = T.open("count", st);
     CUDA_OK(c, sqk_prep(w, st, L));
     if (c->p.lossy) CUDA_OK(c, sqk_rblock(w, c->p.lossy_r, st, L));
     CUDA_OK(c, sqk_count(w, st, L));
     T.close(sp, st);
-    // the chain kernels (MD5, side streams, range coders) are all launched in phase B below; training needs none of them
-    // a sub-wave seen as a wave of its own: descriptors / per-read arrays offset to its first block / read, element
-    // buffers shifted so that the blocks' job-wide element bases (BlockDesc::ebase, shared with the triples) index them
-    auto view = [&](size_t k, int stream, u64 **ea, u64 **eb) {
-        const Sub &u = subs[k];
-        EncWave v = w;
-        v.B = u.b1 - u.b0;
-        v.bd = w.bd + u.b0; v.bs = w.bs + u.b0;
-        v.rbase = d_rbase_sub + rsub_at[k];
-        u32 r0 = rbase[u.b0];
-        v.R = rbase[u.b1] - r0;
-        v.seqoff = w.seqoff + r0; v.idoff = w.idoff + r0; v.acgtoff = w.acgtoff + r0; v.qlen2 = w.qlen2 + r0;
-        v.qoff = w.qoff + r0; v.noff = w.noff + r0; v.tip = w.tip + r0; v.np = w.np + r0; v.ns = w.ns + r0;
-        for (int s = 0; s < ST_COUNT; s++) v.maxbound[s] = u.emax[s];
-        *ea = w.elemA - bd[u.b0].ebase[stream];
-        *eb = w.elemB - bd[u.b0].ebase[stream];
-        return v;
-    };
+    CUDA_OK(c, cudaEventRecord(c->ev[2], st));                       // per-read offsets, tip flags, counts
+    CUDA_OK(c, cudaStreamWaitEvent(s_side, c->ev[2], 0));
+    sp = T.open("side", s_side);
+    CUDA_OK(c, sqk_side(w, s_side, L));
+    T.close(sp, s_side);
+    CUDA_OK(c, cudaEventRecord(c->ev[3], s_side));
+
     if (train_blob) {
+        // the md5 / side kernels launched above are harmless here; only the model replays matter
         int kb[3] = {(int)(2 * c->NS()), c->p.qlevel > 2 ? 20 : 16, 14};
         for (int s = 0; s < ST_COUNT; s++) {
             if (s == ST_NAME && c->p.id_rule) continue;
-            u64 *sorted = nullptr, *ea, *eb;
-            EncWave v = view(0, s, &ea, &eb);
-            CUDA_OK(c, sqk_emit(v, s, ea, st, L));
-            CUDA_OK(c, sqk_sort(v, s, kb[s], ea, eb, &sorted, st, L));
-            CUDA_OK(c, sqk_replay(v, s, sorted, w.triples[s], st, L));
+            u64 *sorted = nullptr;
+            CUDA_OK(c, sqk_emit(w, s, w.elemA, st, L));
+            CUDA_OK(c, sqk_sort(w, s, kb[s], w.elemA, w.elemB, &sorted, st, L));
+            CUDA_OK(c, sqk_replay(w, s, sorted, w.triples[s], st, L));
         }
+        CUDA_OK(c, cudaStreamWaitEvent(st, c->ev[1], 0));
+        CUDA_OK(c, cudaStreamWaitEvent(st, c->ev[3], 0));
         BlockState hb;
         CUDA_OK(c, cudaMemcpyAsync(&hb, w.bs, sizeof hb, cudaMemcpyDeviceToHost, st));
         CUDA_OK(c, cudaStreamSynchronize(st));
@@ -473,45 +430,25 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     static const char *nm_rep[3] = {"seq.replay", "qual.replay", "name.replay"};
     static const char *nm_rc[3] = {"seq.rc", "qual.rc", "name.rc"};
     int keybits[3] = {(int)(2 * c->NS()), c->p.qlevel > 2 ? 20 : 16, 14};
-    // Phase A, throughput: the front end of every stream over every sub-wave, alone on the GPU apart from the MD5 /
-    // side-stream chains (a few hundred resident warps).  Phase B, latency: the three range-coder passes, launched
-    // together into the idle GPU so that the block scheduler spreads their CTAs evenly over the SMs (launched beside
-    // a saturating kernel they pile up on whichever SM frees a slot first, and two dozen serial chains sharing
-    // one SM's issue ports run several times slower; asking for unused shared memory to cap that, as round 1 did,
-    // starves the front-end kernels of L1 and shared memory instead).
+    // quality first: its replay + range-coder chain is the longest
     const int order[3] = {ST_QUAL, ST_SEQ, ST_NAME};
-    for (size_t k = 0; k < subs.size(); k++) {
-        for (int oi = 0; oi < 3; oi++) {
-            int s = order[oi];
-            if (s == ST_NAME && c->p.id_rule) continue;
-            u64 *sorted = nullptr, *ea, *eb;
-            EncWave v = view(k, s, &ea, &eb);
-            sp = T.open(nm_emit[s], st);
-            CUDA_OK(c, sqk_emit(v, s, ea, st, L));
-            T.close(sp, st);
-            sp = T.open(nm_sort[s], st);
-            CUDA_OK(c, sqk_sort(v, s, keybits[s], ea, eb, &sorted, st, L));
-            T.close(sp, st);
-            sp = T.open(nm_rep[s], st);
-            CUDA_OK(c, sqk_replay(v, s, sorted, w.triples[s], st, L));
-            T.close(sp, st);
-        }
-    }
-    CUDA_OK(c, cudaEventRecord(c->ev[7], st));
-    CUDA_OK(c, cudaStreamWaitEvent(s_md5, c->ev[7], 0));
-    sp = T.open("md5", s_md5);
-    CUDA_OK(c, sqk_md5(w, s_md5, L));
-    T.close(sp, s_md5);
-    CUDA_OK(c, cudaEventRecord(c->ev[1], s_md5));
-    CUDA_OK(c, cudaStreamWaitEvent(s_side, c->ev[7], 0));
-    sp = T.open("side", s_side);
-    CUDA_OK(c, sqk_side(w, s_side, L));
-    T.close(sp, s_side);
-    CUDA_OK(c, cudaEventRecord(c->ev[3], s_side));
     for (int oi = 0; oi < 3; oi++) {
         int s = order[oi];
         cudaStream_t s_rc = c->aux[2 + s];
-        CUDA_OK(c, cudaStreamWaitEvent(s_rc, c->ev[7], 0));
+        if (!(s == ST_NAME && c->p.id_rule)) {
+            sp = T.open(nm_emit[s], st);
+            CUDA_OK(c, sqk_emit(w, s, w.elemA, st, L));
+            T.close(sp, st);
+            u64 *sorted = nullptr;
+            sp = T.open(nm_sort[s], st);
+            CUDA_OK(c, sqk_sort(w, s, keybits[s], w.elemA, w.elemB, &sorted, st, L));
+            T.close(sp, st);
+            sp = T.open(nm_rep[s], st);
+            CUDA_OK(c, sqk_replay(w, s, sorted, w.triples[s], st, L));
+            T.close(sp, st);
+        }
+        CUDA_OK(c, cudaEventRecord(c->ev[4 + s], st));
+        CUDA_OK(c, cudaStreamWaitEvent(s_rc, c->ev[4 + s], 0));
         sp = T.open(nm_rc[s], s_rc);
         CUDA_OK(c, sqk_rc(w, s, s_rc, L));
         T.close(sp, s_rc);
@@ -564,24 +501,13 @@ int encode_blocks(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out
     int worst = SQ_OK, i = 0;
     c->last_wave_blocks = 0;
     while (i < n) {
-        // as many blocks as the workspace holds persistently, with room left for a front-end sub-wave of at least
-        // SQ_MIN_SUBWAVE blocks (or of all of them)
-        u64 pers = 64 * 1024, osum = 0;
+        WaveAcc acc;
         int j = i;
-        std::vector<u64> top;                          // the SQ_MIN_SUBWAVE largest per-block front-end costs so far
-        while (j < n && j - i < 60000) {
-            BlkCost k = block_cost(c, blocks[j], host);
-            u64 p = block_persistent(k) + 40;          // + its entries in the per-sub-wave read-base table
-            std::vector<u64> t2(top);
-            t2.push_back(block_transient(c, k));
-            std::sort(t2.begin(), t2.end(), std::greater<u64>());
-            if (t2.size() > SQ_MIN_SUBWAVE) t2.resize(SQ_MIN_SUBWAVE);
-            u64 t = 0;
-            for (u64 v : t2) t += v;
-            if (pers + p + std::max(t, osum + k.obuf) + (2u << 20) > c->arena.cap) break;
-            pers += p;
-            osum += k.obuf;
-            top.swap(t2);
+        while (j < n) {
+            WaveAcc t = acc;
+            t.add(c, block_cost(c, blocks[j], host));
+            if (t.total(c) > c->arena.cap || t.B > 60000) break;
+            acc = t;
             j++;
         }
         if (j == i) { c->err = "a single block does not fit the device workspace"; return SQ_ERR_NOMEM; }
@@ -649,8 +575,9 @@ extern "C" int sq_train_model(sq_ctx *c, const sq_block_in *blocks, int n, uint8
         c->p.lossy = 0;                                     // the snapshot is trained on the original qualities
         c->timer.acc.clear();
         c->launches = 0;
-        BlkCost k = block_cost(c, m, false);
-        if (block_persistent(k) + std::max(block_transient(c, k), k.obuf) + (4u << 20) > c->arena.cap) { c->err = "training sample does not fit the device workspace"; rc = SQ_ERR_NOMEM; }
+        WaveAcc acc;
+        acc.add(c, block_cost(c, m, false));
+        if (acc.total(c) > c->arena.cap) { c->err = "training sample does not fit the device workspace"; rc = SQ_ERR_NOMEM; }
         else rc = encode_wave(c, &m, 1, &dummy, false, d + o_blob);
         c->p = keep;
         c->last_valid = false;

@@ -639,7 +639,7 @@ __global__ void k_snap_init(u8 *blob, u64 name_bytes, u32 nseq, u32 nqual) {
 #define RC_NBUF 8
 #endif
 #ifndef RC_SLEEP
-#define RC_SLEEP 400     // ns the producer sleeps when the ring is full: a spinning producer takes issue slots from the chains sharing its scheduler
+#define RC_SLEEP 0
 #endif
 struct RcState { u64 low; u32 range; u32 nout; };
 
@@ -1272,19 +1272,19 @@ cudaError_t sqk_snap_init(u8 *blob, u64 name_bytes, u32 nseq, u32 nqual, cudaStr
 }
 
 cudaError_t sqk_rc(const EncWave &w, int stream, cudaStream_t st, u64 *launches) {
-    k_rc<<<w.B, 64, 0, st>>>(w.bd, w.bs, w.triples[ST_SEQ], w.triples[ST_QUAL], w.triples[ST_NAME], w.obuf, w.id_rule, stream);
+    k_rc<<<w.B, 64, SQ_CHAIN_SMEM_RC, st>>>(w.bd, w.bs, w.triples[ST_SEQ], w.triples[ST_QUAL], w.triples[ST_NAME], w.obuf, w.id_rule, stream);
     *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t sqk_md5(const EncWave &w, cudaStream_t st, u64 *launches) {
-    k_md5<<<3 * w.B, 32, 0, st>>>(w.bd, w.bs, w.B);
+    k_md5<<<3 * w.B, 32, SQ_CHAIN_SMEM_SMALL, st>>>(w.bd, w.bs, w.B);
     *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t sqk_side(const EncWave &w, cudaStream_t st, u64 *launches) {
-    k_side<<<w.B, 160, 0, st>>>(w.bd, w.bs, w.rbase, w.seqoff, w.tip, w.sidebuf);
+    k_side<<<w.B, 160, SQ_CHAIN_SMEM_SMALL, st>>>(w.bd, w.bs, w.rbase, w.seqoff, w.tip, w.sidebuf);
     *launches += 1;
     return cudaGetLastError();
 }
@@ -1297,8 +1297,14 @@ cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launch
     return cudaGetLastError();
 }
 
-// opt-in shared-memory sizes of the sort kernels
+// Chain kernels are launched on side streams while the main stream keeps every SM busy, and the
+// block scheduler then drops their CTAs onto whichever SM frees a slot first: without a limit two
+// dozen serial chains end up sharing one SM's four issue ports (measured: 6.6x slower).  Asking for
+// shared memory they do not use caps the chains per SM (227 KB / 72 KB = 3, / 36 KB = 6).
 cudaError_t sqk_enc_attrs() {
+    CK(cudaFuncSetAttribute(k_rc, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_RC));
+    CK(cudaFuncSetAttribute(k_md5, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_SMALL));
+    CK(cudaFuncSetAttribute(k_side, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_SMALL));
     CK(cudaFuncSetAttribute(k_sort_hist<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
     CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,

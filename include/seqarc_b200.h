@@ -49,7 +49,7 @@ typedef struct {
     int32_t slevel;        /* SeqArcParam+0x1b54, default 3 -> order-10 base context */
     int32_t qlevel;        /* SeqArcParam+0x1b58, default 2 */
     int32_t id_rule;       /* SeqArcParam+0x18a4 idbin[0]: 1 = rule-based ID path (first ID only) */
-    uint64_t workspace_bytes;  /* device workspace budget; 0 = 88 % of free device memory */
+    uint64_t workspace_bytes;  /* device workspace budget; 0 = 80 % of free device memory */
     void   *stream;        /* cudaStream_t to launch on, or NULL for a private stream */
     int32_t ref_mode;      /* 0: no reference index.  1 (SE) / 2 (PE): the archive is written against a reference
                               index and no read of the block mapped (BASELINE configs[4]): doAlignEncode @0x42d4c0
@@ -137,9 +137,6 @@ int  sq_last_timings(const sq_ctx *c, const char **names, float *ms, int cap);
 uint64_t sq_last_launches(const sq_ctx *c);
 /* how many blocks one wave of the last call held (workspace-limited) */
 int  sq_last_wave_blocks(const sq_ctx *c);
-/* into how many block ranges ("sub-waves") the last encode wave split its context / sort / replay front end; the
- * range-coder pass of each stream runs once over the whole wave whatever this number is */
-int  sq_last_subwaves(const sq_ctx *c);
 
 /* Test hook: copy an intermediate device buffer of the LAST encoded wave to the host.
  * what: 0 = seq triples (u64 cum|freq<<16|tot<<32 per coded base, stream order), 1 = qual triples,

@@ -121,31 +121,6 @@ def test_waves_give_identical_records(fq):
     big.close(); small.close()
 
 
-def test_subwaves_give_identical_records(fq):
-    """A workspace that holds the whole batch persistently but only part of its context / sort / replay front end:
-    the front end runs over several block ranges, the range-coder pass once over all blocks; records do not change."""
-    blocks = [common.synth_block(kind="illumina_pe150", n_templates=1500, seed=70 + i, n_rate=0.002, hash_tail=0.03) for i in range(10)]
-    big = fq.EncapFqzComp(workspace_bytes=2 << 30)
-    a = [common.to_membuf(b) for b in blocks]
-    d1 = fq.DebugInfo()
-    big.doFqzEncode(a, d1)
-    assert d1.wave_blocks == len(blocks) and d1.subwaves == 1
-    seen = set()
-    for mb_ in range(96, 400, 12):
-        small = fq.EncapFqzComp(workspace_bytes=mb_ << 20)
-        b = [common.to_membuf(x) for x in blocks]
-        d2 = fq.DebugInfo()
-        small.doFqzEncode(b, d2)
-        small.close()
-        if d2.wave_blocks == len(blocks):
-            seen.add(d2.subwaves)
-        assert [m.out for m in a] == [m.out for m in b], (mb_, d2.wave_blocks, d2.subwaves)
-    assert any(k > 1 for k in seen) and 1 in seen, seen        # some sizes split the front end, larger ones do not
-    o = po.Oracle()
-    assert a[7].out == o.encode_block(blocks[7])
-    big.close()
-
-
 def test_input_the_reference_cannot_represent_is_rejected(fq):
     codec = fq.EncapFqzComp(workspace_bytes=1 << 30)
     good = ragged_block(7, 300)
