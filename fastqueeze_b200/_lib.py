@@ -18,7 +18,7 @@ STATUS = {0: "SQ_OK", -1: "SQ_ERR_NO_DEVICE", -2: "SQ_ERR_CUDA", -3: "SQ_ERR_ARG
 # every symbol include/seqarc_b200.h declares
 EXPORTS = ["sq_create", "sq_destroy", "sq_last_error", "sq_load_model", "sq_model_size", "sq_train_model", "sq_encode_blocks",
            "sq_encode_blocks_dev", "sq_decode_blocks", "sq_decode_blocks_dev", "sq_rblock", "sq_last_timings",
-           "sq_last_launches", "sq_last_wave_blocks", "sq_debug_fetch", "sq_version"]
+           "sq_last_launches", "sq_last_wave_blocks", "sq_debug_fetch", "sq_device_count", "sq_version"]
 
 
 class SqParams(C.Structure):
@@ -92,6 +92,8 @@ def lib():
     L.sq_last_wave_blocks.argtypes = [C.c_void_p]
     L.sq_debug_fetch.restype = C.c_int
     L.sq_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.sq_device_count.restype = C.c_int
+    L.sq_device_count.argtypes = []
     L.sq_version.restype = C.c_char_p
     L.sq_version.argtypes = []
     _lib = L

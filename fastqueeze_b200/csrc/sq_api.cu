@@ -99,6 +99,11 @@ static int ensure_pin(sq_ctx *c, u64 bytes) {
     return SQ_OK;
 }
 
+extern "C" int sq_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" const char *sq_version(void) { return "seqarc-b200 0.1 (SeqArc v1.6 stream format)"; }
 
 extern "C" const char *sq_last_error(const sq_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }

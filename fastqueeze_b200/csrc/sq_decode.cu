@@ -11,7 +11,6 @@
 // block): the chains are L2/HBM-latency bound by construction.
 #include "sq_common.cuh"
 #include "sq_kernels.h"
-#include <cstdlib>
 #include "sq_md5.cuh"
 #include <cstdio>
 
@@ -1233,20 +1232,20 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
         int need = ctas * ((int)sizeof(MainSmem) + 1024 + 256);
         int carve = (int)((100ll * need + smem_sm - 1) / smem_sm);
         if (carve > 100) carve = 100;
-        const char *e = getenv("SQ_DEC_CARVEOUT");
-        if (e) carve = atoi(e);
-        if (carve >= 0) {
+        {
             cudaFuncSetAttribute(k_dec_main<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(k_dec_main<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(k_dec_main<3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         }
     }
     k_dec_len<<<B, 32, 0, st>>>(w.db);
-    // The MD5s are verified inside k_dec_main (lane 0 of the names warp chases the other two warps: -0.7 s of
-    // 10.7 s on the full job); SQ_DEC_INLINE_MD5=0 brings back the separate k_dec_md5 pass.
-    static int inl = -1;
-    if (inl < 0) { const char *e = getenv("SQ_DEC_INLINE_MD5"); inl = e ? atoi(e) != 0 : 1; }
-    const int inline_md5 = (w.md5 && inl) ? 1 : 0;
+    // The MD5s are verified inside k_dec_main (lane 0 of the names warp chases the other two warps); k_dec_md5 is the
+    // separate pass kept for builds with -DSQ_DEC_SEPARATE_MD5.
+#ifdef SQ_DEC_SEPARATE_MD5
+    const int inline_md5 = 0;
+#else
+    const int inline_md5 = w.md5 ? 1 : 0;
+#endif
     if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
     else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
     else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);

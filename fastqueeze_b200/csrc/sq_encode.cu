@@ -161,7 +161,7 @@ __global__ void k_qual_pass(const BlockDesc *bd, BlockState *bs, const u32 *rbas
         for (u32 i0 = 0; i0 < len; i0 += 32) {
             u32 i = i0 + lane;
             u32 c = (i < len) ? q[i] : (u32)'#';
-            if (i < len && (u8)(c - 33) > 94) bad = true;
+            if (i < len && (u8)(c - 33) > 93) bad = true;      // '!' .. '~': symbol 94 is the read terminator
             u32 m = __ballot_sync(FULL, c != '#');
             if (m) len2 = i0 + 32 - __clz(m);
         }
@@ -256,6 +256,7 @@ __global__ void k_name_pass(const BlockDesc *bd, BlockState *bs, const u32 *rbas
         int ctx = v % 8192;
         if (ctx < 0) { bad = true; ctx = 0; }
         u32 ch = name[i];
+        if (ch & 0x80) bad = true;                      // the name model codes ch & 0x7f (@0x4215b0): bit 7 would not survive
         dst[o] = el_make(NK_MIDDLE + (u32)ctx, ch & 0x7f, o); o++;
         if (ch == ' ' && nv.last(j) != ' ') j++;
         if (ch != ' ' && nv.last(j) == ' ') j--;

@@ -1,5 +1,10 @@
 #include "arc_file.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstring>
 
@@ -115,16 +120,24 @@ static int get_vint(const uint8_t *p, const uint8_t *end, uint64_t *v) {
     return n;
 }
 
+ArcReader::~ArcReader() {
+    if (base && size) munmap((void *)base, size);
+}
+
 bool ArcReader::load(const std::string &path) {
-    FILE *f = fopen(path.c_str(), "rb");
-    if (!f) { err = "cannot open " + path; return false; }
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    data.resize(n);
-    if (n && fread(data.data(), 1, n, f) != (size_t)n) { fclose(f); err = "short read"; return false; }
-    fclose(f);
-    const uint8_t *d = data.data(), *end = d + data.size();
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) { err = "cannot open " + path; return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); err = "cannot stat " + path; return false; }
+    long n = (long)st.st_size;
+    if (n > 0) {
+        void *m = mmap(nullptr, (size_t)n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { ::close(fd); err = "cannot map " + path; return false; }
+        base = (const uint8_t *)m;
+        size = (size_t)n;
+    }
+    ::close(fd);
+    const uint8_t *d = base, *end = d + size;
     if (n < 16 || memcmp(d, ".arc", 4) != 0 || d[4] != 1 || d[5] != 6) { err = "not a SeqArc v1.6 archive"; return false; }
     uint64_t tag, sz;
     const uint8_t *q = d + 7;
@@ -179,7 +192,7 @@ bool ArcReader::load(const std::string &path) {
         b.arc_off = rd(x + 16, 8);
         b.src_off[0] = rd(x + 24, 8);
         if (p.pe) b.src_off[1] = rd(x + 32, 8);
-        if (b.arc_off + b.len > data.size()) { err = "block index points outside the file"; return false; }
+        if (b.arc_off + b.len > size) { err = "block index points outside the file"; return false; }
         idx.push_back(b);
     }
     return true;

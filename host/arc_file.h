@@ -50,9 +50,14 @@ private:
 struct ArcReader {
     ArcParams p;
     std::vector<BlockIndex> idx;
-    std::vector<uint8_t> data;     // whole file
+    const uint8_t *base = nullptr; // the file, mapped read-only (block records are handed to the GPU from here)
+    size_t size = 0;
     std::string err;
     bool load(const std::string &path);
+    ArcReader() = default;
+    ArcReader(const ArcReader &) = delete;
+    ArcReader &operator=(const ArcReader &) = delete;
+    ~ArcReader();
 };
 
 }  // namespace sqhost

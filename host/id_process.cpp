@@ -39,10 +39,12 @@ static bool all_digits(const std::string &s) {
 // analysisPEType @0x430f50
 static int pe_type(const std::string &a, const std::string &b) {
     if (a.size() == b.size() && memcmp(a.data(), b.data(), a.size()) == 0) return 1;
+    // (the reference compares a's prefix against b without looking at b's length; an ID shorter than that prefix
+    // cannot match, and is not read past its end here)
     if (!a.empty() && !b.empty() && a[a.size() - 1] == '1' && b[b.size() - 1] == '2' &&
-        memcmp(a.data(), b.data(), a.size() - 1) == 0) return 2;
+        b.size() >= a.size() - 1 && a.compare(0, a.size() - 1, b, 0, a.size() - 1) == 0) return 2;
     size_t p = a.find("length");
-    if (p != std::string::npos && (int)p != -1 && memcmp(a.data(), b.data(), p) == 0) return 3;
+    if (p != std::string::npos && (int)p != -1 && b.size() >= p && a.compare(0, p, b, 0, p) == 0) return 3;
     return 0;
 }
 

@@ -10,7 +10,12 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <fcntl.h>
 #include <future>
+#include <map>
+#include <unistd.h>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -32,7 +37,10 @@ struct Opt {
     double lossy_r = 0;
     std::string in1, in2, out, arc;
     std::string ref;            // reference FASTA given on the command line (SeqArc -c [ref.fa] ... / -d [ref.fa] x.arc)
-    int block_mb = 50, slevel = 3, qlevel = 2, device = 0, batch = 0;
+    int block_mb = 50, slevel = 3, qlevel = 2, batch = 0;
+    std::vector<int> devices;   // -g 0,1,...  (default: every visible GPU)
+    int force_usemodel = -1;    // --usemodel 0|1: test hook (the reference decides from the input size alone)
+    bool parse_only = false;    // --parse-only: print what the command line means and exit (no GPU needed)
     bool verbose = false;
 };
 
@@ -66,10 +74,10 @@ static bool exists(const std::string &p) { struct stat st; return stat(p.c_str()
 
 static void die(const std::string &m) { fprintf(stderr, "seqarc_b200: %s\n", m.c_str()); exit(1); }
 
-static sq_ctx *make_ctx(const Opt &o, bool usemodel, bool lossy, double r, bool md5, int id_rule, int ref_mode = 0) {
+static sq_ctx *make_ctx(const Opt &o, int device, bool usemodel, bool lossy, double r, bool md5, int id_rule, int ref_mode = 0) {
     sq_params p{};
     p.ref_mode = ref_mode;
-    p.device = o.device; p.usemodel = usemodel; p.lossy = lossy; p.lossy_r = r; p.md5 = md5;
+    p.device = device; p.usemodel = usemodel; p.lossy = lossy; p.lossy_r = r; p.md5 = md5;
     p.slevel = o.slevel; p.qlevel = o.qlevel; p.id_rule = id_rule;
     sq_ctx *c = nullptr;
     if (sq_create(&p, &c) != SQ_OK) die(std::string("sq_create: ") + sq_last_error(nullptr));
@@ -114,6 +122,27 @@ static void sample_blocks(const Opt &o, std::vector<MemBuf> &out) {
     }
 }
 
+// ---- the job sharded over the GPUs of the box ------------------------------------------------------------
+// Blocks are independent (every model resets per block), so the only thing the GPUs share is the ORDER of the records
+// in the archive: the reference appends each block at "previous offset + previous length" (addBlockPEInfo @0x412f30,
+// @0x412f6d-0x412f76), and its -t 1 output is the byte-exact target.  One host thread and one sq_ctx per GPU; the
+// reader deals out consecutive batches of blocks, the writer takes the encoded batches back in batch order.
+static std::vector<int> pick_devices(const Opt &o) {
+    int n = sq_device_count();
+    if (n <= 0) die("no CUDA device (this program has no CPU path)");
+    std::vector<int> d = o.devices;
+    if (d.empty()) for (int i = 0; i < n; i++) d.push_back(i);
+    for (int x : d) if (x < 0 || x >= n) die("device ordinal out of range in -g");
+    return d;
+}
+
+struct EncBatch {
+    uint64_t seq = 0;
+    std::vector<MemBuf> mbs;
+    std::vector<std::vector<uint8_t>> recs;
+    std::vector<uint64_t> lens;
+};
+
 static int do_compress(const Opt &o) {
     std::string arcname = o.out + ".arc";
     if (exists(arcname) && !o.force) die(arcname + " exists (use -f)");
@@ -125,7 +154,7 @@ static int do_compress(const Opt &o) {
     long long est = (long long)((float)(long long)total * 0.0023947358f);
     if (gz) est = (long long)((float)est * 2.73f);
     bool usemodel = est > 33693269 && o.qlevel <= 2;
-    if (getenv("SQ_FORCE_USEMODEL")) usemodel = atoi(getenv("SQ_FORCE_USEMODEL")) != 0;
+    if (o.force_usemodel >= 0) usemodel = o.force_usemodel != 0;
     ArcParams ap;
     ap.pe = pe; ap.usemodel = usemodel; ap.lossy = o.lossy; ap.md5 = o.md5;
     ap.name1 = base_name(o.in1); ap.name2 = base_name(o.in2);
@@ -161,84 +190,184 @@ static int do_compress(const Opt &o) {
         if (okbins) okbins = analyse_id_bins(m, pe, ap.idbin);
     ap.comment = !sample.empty() && sample[0].comment;
     if (o.verbose) fprintf(stderr, "bOrderBin %d petype %d\n", ap.idbin[0], ap.idbin[1]);
-    sq_ctx *c = make_ctx(o, usemodel, o.lossy, o.lossy_r, o.md5, ap.idbin[0], ap.has_ref ? (pe ? 2 : 1) : 0);
+    const std::vector<int> devs = pick_devices(o);
+    const int ndev = (int)devs.size();
+    const int ref_mode = ap.has_ref ? (pe ? 2 : 1) : 0;
+    std::vector<sq_ctx *> ctx(ndev, nullptr);
+    {
+        std::vector<std::thread> th;                   // workspace allocation of the devices in parallel
+        for (int d = 0; d < ndev; d++) th.emplace_back([&, d]() { ctx[d] = make_ctx(o, devs[d], usemodel, o.lossy, o.lossy_r, o.md5, ap.idbin[0], ref_mode); });
+        for (auto &t : th) t.join();
+    }
     if (usemodel) {
         std::vector<sq_block_in> in;
         for (auto &m : sample) in.push_back(as_in(m));
-        ap.model.resize(sq_model_size(c));
-        if (sq_train_model(c, in.data(), (int)in.size(), ap.model.data(), ap.model.size()) != SQ_OK)
-            die(std::string("training: ") + sq_last_error(c));
-        if (sq_load_model(c, ap.model.data(), ap.model.size()) != SQ_OK) die(sq_last_error(c));
+        ap.model.resize(sq_model_size(ctx[0]));
+        if (sq_train_model(ctx[0], in.data(), (int)in.size(), ap.model.data(), ap.model.size()) != SQ_OK)
+            die(std::string("training: ") + sq_last_error(ctx[0]));
+        for (int d = 0; d < ndev; d++)
+            if (sq_load_model(ctx[d], ap.model.data(), ap.model.size()) != SQ_OK) die(sq_last_error(ctx[d]));
     }
+    std::vector<MemBuf>().swap(sample);
     BlockReader rd(o.in1, o.in2, (uint64_t)o.block_mb << 20);
     if (!rd.ok()) die("cannot open input");
     ArcWriter wr;
     if (!wr.open(arcname)) die("cannot create " + arcname);
-    int batch = o.batch > 0 ? o.batch : 128;      // blocks per GPU call: the chain kernels want as many blocks per wave as the workspace holds
-    std::vector<MemBuf> mbs;
-    std::vector<std::vector<uint8_t>> recs;
-    uint64_t nblocks = 0, in_bytes = 0;
+    // Blocks per GPU call.  The chain kernels take the same time for one block as for a wave of them, so a batch
+    // should be this GPU's whole share of the job when the workspace holds it (~0.75 GB per default-size block).
+    uint64_t est_blocks = std::max<uint64_t>(1, ((gz ? total * 4 : total) + ((uint64_t)o.block_mb << 20) - 1) / ((uint64_t)o.block_mb << 20));
+    uint64_t cap_blocks = std::max<uint64_t>(1, (uint64_t)(100.0 * 50 / std::max(1, o.block_mb)));
+    int batch = o.batch > 0 ? o.batch : (int)std::min<uint64_t>(cap_blocks, (est_blocks + ndev - 1) / ndev);
     auto t0 = std::chrono::steady_clock::now();
-    // Host pipeline: the reader cuts block texts sequentially (cheap), a pool parses them into MemBufs in parallel,
-    // and the next batch is cut + parsed while the GPU encodes the current one.
-    const bool rd_pe = pe;
-    auto load_batch = [&rd, batch, rd_pe]() {
-        std::vector<BlockReader::Raw> raws;
-        while ((int)raws.size() < batch) {
-            raws.emplace_back();
-            if (!rd.next_raw(raws.back())) { raws.pop_back(); break; }
-        }
-        std::vector<MemBuf> out(raws.size());
-        std::string err;
-        std::mutex mu;
-        std::atomic<size_t> next{0};
-        unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)raws.size()}));
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nt; t++)
-            pool.emplace_back([&]() {
-                for (size_t i; (i = next.fetch_add(1)) < raws.size();) {
-                    try { BlockReader::parse_raw(raws[i], rd_pe, out[i]); }
-                    catch (const std::exception &e) { std::lock_guard<std::mutex> g(mu); if (err.empty()) err = e.what(); }
-                    std::vector<char>().swap(raws[i].t1);
-                    std::vector<char>().swap(raws[i].t2);
+
+    // reader: cuts block texts sequentially, a pool parses them into MemBufs, batches go to whichever GPU is free
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<EncBatch> ready;                        // parsed, waiting for a GPU
+    std::map<uint64_t, EncBatch> done;                 // encoded, waiting for the writer
+    bool eof = false;
+    int inflight = 0;                                  // batches a GPU thread holds
+    std::string failure;
+    const size_t max_ready = (size_t)ndev + 1;
+    std::thread reader([&]() {
+        uint64_t seq = 0;
+        try {
+            for (;;) {
+                std::vector<BlockReader::Raw> raws;
+                while ((int)raws.size() < batch) {
+                    raws.emplace_back();
+                    if (!rd.next_raw(raws.back())) { raws.pop_back(); break; }
                 }
-            });
-        for (auto &th : pool) th.join();
-        if (!err.empty()) throw std::runtime_error(err);
-        return out;
-    };
-    std::future<std::vector<MemBuf>> ahead = std::async(std::launch::async, load_batch);
+                if (raws.empty()) break;
+                EncBatch eb;
+                eb.seq = seq++;
+                eb.mbs.resize(raws.size());
+                std::string err;
+                std::mutex emu;
+                std::atomic<size_t> next{0};
+                unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)raws.size()}));
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < nt; t++)
+                    pool.emplace_back([&]() {
+                        for (size_t i; (i = next.fetch_add(1)) < raws.size();) {
+                            try { BlockReader::parse_raw(raws[i], pe, eb.mbs[i]); }
+                            catch (const std::exception &e) { std::lock_guard<std::mutex> g(emu); if (err.empty()) err = e.what(); }
+                            std::vector<char>().swap(raws[i].t1);
+                            std::vector<char>().swap(raws[i].t2);
+                        }
+                    });
+                for (auto &th : pool) th.join();
+                if (!err.empty()) throw std::runtime_error(err);
+                for (auto &m : eb.mbs)
+                    if (m.comment != ap.comment) throw std::runtime_error("'+' lines must be all bare or all a copy of the ID");
+                bool last = (int)eb.mbs.size() < batch;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&]() { return ready.size() < max_ready || !failure.empty(); });
+                    if (!failure.empty()) break;
+                    ready.push_back(std::move(eb));
+                }
+                cv.notify_all();
+                if (last) break;
+            }
+        } catch (const std::exception &e) {
+            std::lock_guard<std::mutex> g(mu);
+            if (failure.empty()) failure = e.what();
+        }
+        { std::lock_guard<std::mutex> g(mu); eof = true; }
+        cv.notify_all();
+    });
+    std::vector<std::thread> gpus;
+    for (int d = 0; d < ndev; d++)
+        gpus.emplace_back([&, d]() {
+            for (;;) {
+                EncBatch eb;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&]() { return !ready.empty() || eof || !failure.empty(); });
+                    if (!failure.empty() || ready.empty()) return;
+                    eb = std::move(ready.front());
+                    ready.pop_front();
+                    inflight++;
+                }
+                cv.notify_all();
+                int n = (int)eb.mbs.size();
+                std::vector<sq_block_in> in(n);
+                std::vector<sq_block_out> out(n);
+                eb.recs.resize(n);
+                eb.lens.resize(n);
+                for (int i = 0; i < n; i++) {
+                    in[i] = as_in(eb.mbs[i]);
+                    eb.recs[i].resize(eb.mbs[i].ids.size() + 2 * eb.mbs[i].seq.size() + 8 * (size_t)eb.mbs[i].nreads() + 4096);
+                    out[i] = {eb.recs[i].data(), eb.recs[i].size(), 0, 0};
+                }
+                int rc = sq_encode_blocks(ctx[d], in.data(), n, out.data());
+                if (rc != SQ_OK) {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (failure.empty()) failure = std::string("encode: ") + sq_last_error(ctx[d]) + " (status " + std::to_string(rc) + ")";
+                    inflight--;
+                    cv.notify_all();
+                    return;
+                }
+                // rule-based IDs: what the decoder will regenerate from each block's first ID must be what went in
+                if (ap.idbin[0]) {
+                    for (int i = 0; i < n && rc == SQ_OK; i++) {
+                        const MemBuf &m = eb.mbs[i];
+                        std::vector<uint8_t> pay(2 + (m.nreads() ? m.idlen[0] : 0)), ids;
+                        std::vector<uint16_t> idl;
+                        if (m.nreads()) { pay[0] = (uint8_t)m.idlen[0]; pay[1] = (uint8_t)(m.idlen[0] >> 8); memcpy(pay.data() + 2, m.ids.data(), m.idlen[0]); }
+                        if (!decode_ids(pay.data(), pay.size(), ap.idbin, m.seqlen.data(), m.nreads(), ids, idl) || ids != m.ids || idl != m.idlen) {
+                            std::lock_guard<std::mutex> g(mu);
+                            if (failure.empty()) failure = "read IDs are not reproduced by the ID rules found in the head of the input (block " + std::to_string(eb.seq * batch + i) + ")";
+                            rc = -1;
+                        }
+                    }
+                    if (rc != SQ_OK) { { std::lock_guard<std::mutex> g(mu); inflight--; } cv.notify_all(); return; }
+                }
+                for (int i = 0; i < n; i++) {
+                    eb.lens[i] = out[i].len;
+                    MemBuf &m = eb.mbs[i];          // only the index data is still needed
+                    std::vector<uint8_t>().swap(m.ids); std::vector<uint8_t>().swap(m.seq); std::vector<uint8_t>().swap(m.qual);
+                }
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    uint64_t k = eb.seq;
+                    done.emplace(k, std::move(eb));
+                    inflight--;
+                }
+                cv.notify_all();
+            }
+        });
+    // writer (this thread): the ordered gather
+    uint64_t nblocks = 0, in_bytes = 0, want = 0;
     for (;;) {
-        mbs = ahead.get();
-        if (mbs.empty()) break;
-        bool full = (int)mbs.size() == batch;
-        if (full) ahead = std::async(std::launch::async, load_batch);      // overlaps the GPU work below
-        for (auto &m : mbs)
-            if (m.comment != ap.comment) die("'+' lines must be all bare or all a copy of the ID");
-        int n = (int)mbs.size();
-        std::vector<sq_block_in> in(n);
-        std::vector<sq_block_out> out(n);
-        recs.resize(n);
-        for (int i = 0; i < n; i++) {
-            in[i] = as_in(mbs[i]);
-            recs[i].resize(mbs[i].ids.size() + 2 * mbs[i].seq.size() + 8 * (size_t)mbs[i].nreads() + 4096);
-            out[i] = {recs[i].data(), recs[i].size(), 0, 0};
+        EncBatch eb;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&]() { return done.count(want) || !failure.empty() || (eof && ready.empty() && inflight == 0); });
+            if (!failure.empty()) break;
+            auto it = done.find(want);
+            if (it == done.end()) break;               // input exhausted and every batch written
+            eb = std::move(it->second);
+            done.erase(it);
         }
-        int rc = sq_encode_blocks(c, in.data(), n, out.data());
-        if (rc != SQ_OK) die(std::string("encode: ") + sq_last_error(c) + " (status " + std::to_string(rc) + ")");
-        for (int i = 0; i < n; i++) {
-            wr.add_block(recs[i].data(), out[i].len, mbs[i].src_bytes, mbs[i].src_off, mbs[i].longflag);
-            in_bytes += mbs[i].src_bytes[0] + mbs[i].src_bytes[1];
+        for (size_t i = 0; i < eb.mbs.size(); i++) {
+            wr.add_block(eb.recs[i].data(), eb.lens[i], eb.mbs[i].src_bytes, eb.mbs[i].src_off, eb.mbs[i].longflag);
+            in_bytes += eb.mbs[i].src_bytes[0] + eb.mbs[i].src_bytes[1];
         }
-        nblocks += n;
-        if (!full) break;
+        nblocks += eb.mbs.size();
+        want++;
     }
+    cv.notify_all();
+    reader.join();
+    for (auto &t : gpus) if (t.joinable()) t.join();
+    if (!failure.empty()) die(failure);
     if (!wr.finish(ap)) die("write failed");
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (o.verbose)
-        fprintf(stderr, "blocks %llu  in %llu B  out %llu B  ratio %.3f  usemodel %d  %.2f s\n", (unsigned long long)nblocks,
-                (unsigned long long)in_bytes, (unsigned long long)wr.bytes(), wr.bytes() ? (double)in_bytes / wr.bytes() : 0.0, (int)usemodel, s);
-    sq_destroy(c);
+        fprintf(stderr, "blocks %llu  in %llu B  out %llu B  ratio %.3f  usemodel %d  gpus %d  batch %d  %.2f s\n", (unsigned long long)nblocks,
+                (unsigned long long)in_bytes, (unsigned long long)wr.bytes(), wr.bytes() ? (double)in_bytes / wr.bytes() : 0.0, (int)usemodel, ndev, batch, s);
+    for (auto c : ctx) sq_destroy(c);
     return 0;
 }
 
@@ -273,84 +402,123 @@ static bool find_id_payload(const uint8_t *rec, uint64_t len, bool md5, const ui
     return false;
 }
 
+// Decompress: the block index gives every block's place in the output files (source offsets), so the GPUs take
+// contiguous block ranges (ranges keep a GPU's records adjacent in the mapped archive) and write where the index says.
 static int do_decompress(const Opt &o) {
     ArcReader ar;
     if (!ar.load(o.arc)) die(ar.err);
     const bool rule = ar.p.idbin[0] != 0;
     bool pe = ar.p.pe;
-    std::string n1 = pe ? o.out + "_1.fastq" : o.out + ".fastq", n2 = o.out + "_2.fastq";
+    // without a prefix the outputs take the names of the compressed inputs (README.md:97; measured: SeqArc -d x.arc
+    // writes a_1.fq / a_2.fq into the current directory)
+    std::string n1, n2;
+    if (o.out.empty()) { n1 = ar.p.name1; n2 = ar.p.name2; if (n1.empty() || (pe && n2.empty())) die("the archive holds no input names; give an output prefix"); }
+    else { n1 = pe ? o.out + "_1.fastq" : o.out + ".fastq"; n2 = o.out + "_2.fastq"; }
     if (!o.force && (exists(n1) || (pe && exists(n2)))) die("output exists (use -f)");
-    sq_ctx *c = make_ctx(o, ar.p.usemodel, ar.p.lossy, 1.5, ar.p.md5, rule);
-    if (ar.p.usemodel && sq_load_model(c, ar.p.model.data(), ar.p.model.size()) != SQ_OK) die(sq_last_error(c));
-    FILE *f1 = fopen(n1.c_str(), "wb"), *f2 = pe ? fopen(n2.c_str(), "wb") : nullptr;
-    if (!f1 || (pe && !f2)) die("cannot create output");
-    int batch = o.batch > 0 ? o.batch : 128;      // blocks per GPU call: the chain kernels want as many blocks per wave as the workspace holds
-    std::string o1, o2;
-    for (size_t b0 = 0; b0 < ar.idx.size(); b0 += batch) {
-        int n = (int)std::min<size_t>(batch, ar.idx.size() - b0);
-        std::vector<const uint8_t *> recs(n);
-        std::vector<uint64_t> lens(n);
-        std::vector<sq_block_dec> dec(n);
-        std::vector<MemBuf> mbs(n);
-        for (int i = 0; i < n; i++) {
-            const BlockIndex &bi = ar.idx[b0 + i];
-            recs[i] = ar.data.data() + bi.arc_off;
-            lens[i] = bi.len;
-            uint64_t src = (uint64_t)bi.src_bytes[0] + bi.src_bytes[1];
-            MemBuf &m = mbs[i];
-            m.ids.resize(src + 64); m.seq.resize(src / 2 + 64); m.qual.resize(src / 2 + 64);
-            uint32_t rcap = (uint32_t)(src / 6 + 16);
-            m.idlen.resize(rcap); m.seqlen.resize(rcap);
-            dec[i] = {m.ids.data(), m.ids.size(), m.seq.data(), m.qual.data(), m.seq.size(), m.idlen.data(), m.seqlen.data(), rcap, 0, 0, 0, 0,
-                      bi.longflag ? 1 : 0};
+    const std::vector<int> devs0 = pick_devices(o);
+    const size_t nb = ar.idx.size();
+    const int ndev = (int)std::max<size_t>(1, std::min<size_t>(devs0.size(), nb));
+    std::vector<int> devs(devs0.begin(), devs0.begin() + ndev);
+    int fd1 = ::open(n1.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644), fd2 = pe ? ::open(n2.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644) : -1;
+    if (fd1 < 0 || (pe && fd2 < 0)) die("cannot create output");
+    std::mutex mu;
+    std::string failure;
+    auto fail = [&](const std::string &m) { std::lock_guard<std::mutex> g(mu); if (failure.empty()) failure = m; };
+    auto pwrite_all = [&](int fd, const std::string &t, uint64_t off) {
+        size_t done = 0;
+        while (done < t.size()) {
+            ssize_t k = ::pwrite(fd, t.data() + done, t.size() - done, (off_t)(off + done));
+            if (k <= 0) { fail("write failed"); return; }
+            done += (size_t)k;
         }
-        int rc = sq_decode_blocks(c, recs.data(), lens.data(), n, dec.data());
-        if (rc != SQ_OK) {
-            const char *w = rc == SQ_ERR_MD5_NAME ? "Name md5 unequal" : rc == SQ_ERR_MD5_SEQ ? "Seq md5 unequal" : rc == SQ_ERR_MD5_QUAL ? "Qual md5 unequal" : sq_last_error(c);
-            die(std::string("decode: ") + w);
-        }
-        // regenerate rule-based IDs and render the FASTQ text of the batch's blocks in parallel, then write in order
-        std::vector<std::string> t1(n), t2(n);
-        std::string err;
-        std::mutex mu;
-        std::atomic<int> next{0};
-        auto work = [&]() {
-            for (int i; (i = next.fetch_add(1)) < n;) {
-                MemBuf &m = mbs[i];
-                m.idlen.resize(dec[i].nreads); m.seqlen.resize(dec[i].nreads);
-                const char *bad = nullptr;
-                if (rule) {               // IDProcess::decodeIDS @0x430610: regenerate the IDs from the block's first ID
-                    const uint8_t *pay = nullptr, *md5 = nullptr;
-                    size_t plen = 0;
-                    if (!find_id_payload(recs[i], lens[i], ar.p.md5, &pay, &plen, &md5)) bad = "decode: block without an ID stream";
-                    else {
-                        m.ids.clear(); m.idlen.clear();
-                        if (!decode_ids(pay, plen, ar.p.idbin, m.seqlen.data(), dec[i].nreads, m.ids, m.idlen)) bad = "decode: bad rule-based ID record";
-                        else if (md5) {
-                            uint8_t dig[16];
-                            md5_digest(m.ids.data(), m.ids.size(), dig);
-                            if (memcmp(dig, md5, 16) != 0) bad = "decode: Name md5 unequal";
-                        }
-                    }
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> gpus;
+    for (int d = 0; d < ndev; d++)
+        gpus.emplace_back([&, d]() {
+            size_t lo = nb * d / ndev, hi = nb * (d + 1) / ndev;      // this GPU's contiguous block range
+            if (lo >= hi) return;
+            sq_ctx *c = make_ctx(o, devs[d], ar.p.usemodel, ar.p.lossy, 1.5, ar.p.md5, rule);
+            if (ar.p.usemodel && sq_load_model(c, ar.p.model.data(), ar.p.model.size()) != SQ_OK) { fail(sq_last_error(c)); sq_destroy(c); return; }
+            // blocks per GPU call: the chain kernels take the same time for one block as for a whole wave, so as many as
+            // the decoder's workspace is sure to hold (~0.17 GB per default-size block with the host buffers)
+            size_t batch = o.batch > 0 ? (size_t)o.batch : std::max<size_t>(1, (size_t)(600.0 * 50 / std::max(1, o.block_mb)));
+            std::thread writer;                        // renders / writes batch k while the GPU decodes batch k + 1
+            for (size_t b0 = lo; b0 < hi && failure.empty(); b0 += batch) {
+                int n = (int)std::min<size_t>(batch, hi - b0);
+                auto recs = std::make_shared<std::vector<const uint8_t *>>(n);
+                auto lens = std::make_shared<std::vector<uint64_t>>(n);
+                auto dec = std::make_shared<std::vector<sq_block_dec>>(n);
+                auto mbs = std::make_shared<std::vector<MemBuf>>(n);
+                for (int i = 0; i < n; i++) {
+                    const BlockIndex &bi = ar.idx[b0 + i];
+                    (*recs)[i] = ar.base + bi.arc_off;
+                    (*lens)[i] = bi.len;
+                    uint64_t src = (uint64_t)bi.src_bytes[0] + bi.src_bytes[1];
+                    MemBuf &m = (*mbs)[i];
+                    m.ids.resize(src + 64); m.seq.resize(src / 2 + 64); m.qual.resize(src / 2 + 64);
+                    uint32_t rcap = (uint32_t)(src / 6 + 16);
+                    m.idlen.resize(rcap); m.seqlen.resize(rcap);
+                    (*dec)[i] = {m.ids.data(), m.ids.size(), m.seq.data(), m.qual.data(), m.seq.size(), m.idlen.data(), m.seqlen.data(), rcap, 0, 0, 0, 0,
+                                 bi.longflag ? 1 : 0};
                 }
-                if (bad) { std::lock_guard<std::mutex> g(mu); if (err.empty()) err = bad; continue; }
-                m.comment = ar.p.comment;
-                render_block(m, pe, t1[i], t2[i]);
+                int rc = sq_decode_blocks(c, recs->data(), lens->data(), n, dec->data());
+                if (rc != SQ_OK) {
+                    const char *w = rc == SQ_ERR_MD5_NAME ? "Name md5 unequal" : rc == SQ_ERR_MD5_SEQ ? "Seq md5 unequal" : rc == SQ_ERR_MD5_QUAL ? "Qual md5 unequal" : sq_last_error(c);
+                    fail(std::string("decode: ") + w);
+                    break;
+                }
+                if (writer.joinable()) writer.join();
+                writer = std::thread([&, recs, lens, dec, mbs, b0, n]() {
+                    // regenerate rule-based IDs, render the FASTQ text of the batch's blocks in parallel, write at the recorded offsets
+                    std::atomic<int> next{0};
+                    auto work = [&]() {
+                        std::string t1, t2;
+                        for (int i; (i = next.fetch_add(1)) < n;) {
+                            MemBuf &m = (*mbs)[i];
+                            const sq_block_dec &dd = (*dec)[i];
+                            m.idlen.resize(dd.nreads); m.seqlen.resize(dd.nreads);
+                            const char *bad = nullptr;
+                            if (rule) {               // IDProcess::decodeIDS @0x430610: regenerate the IDs from the block's first ID
+                                const uint8_t *pay = nullptr, *md5 = nullptr;
+                                size_t plen = 0;
+                                if (!find_id_payload((*recs)[i], (*lens)[i], ar.p.md5, &pay, &plen, &md5)) bad = "decode: block without an ID stream";
+                                else {
+                                    m.ids.clear(); m.idlen.clear();
+                                    if (!decode_ids(pay, plen, ar.p.idbin, m.seqlen.data(), dd.nreads, m.ids, m.idlen)) bad = "decode: bad rule-based ID record";
+                                    else if (md5) {
+                                        uint8_t dig[16];
+                                        md5_digest(m.ids.data(), m.ids.size(), dig);
+                                        if (memcmp(dig, md5, 16) != 0) bad = "decode: Name md5 unequal";
+                                    }
+                                }
+                            } else m.ids.resize(dd.idbytes);
+                            if (bad) { fail(bad); continue; }
+                            m.seq.resize(dd.seqbytes); m.qual.resize(dd.seqbytes);
+                            m.comment = ar.p.comment;
+                            render_block(m, pe, t1, t2);
+                            const BlockIndex &bi = ar.idx[b0 + i];
+                            if (t1.size() != bi.src_bytes[0] || (pe && t2.size() != bi.src_bytes[1])) { fail("decode len is not equal org len"); continue; }
+                            pwrite_all(fd1, t1, bi.src_off[0]);
+                            if (pe) pwrite_all(fd2, t2, bi.src_off[1]);
+                            MemBuf().ids.swap(m.ids); MemBuf().seq.swap(m.seq); MemBuf().qual.swap(m.qual);
+                        }
+                    };
+                    unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)n}));
+                    std::vector<std::thread> pool;
+                    for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
+                    for (auto &th : pool) th.join();
+                });
             }
-        };
-        unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)n}));
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
-        for (auto &th : pool) th.join();
-        if (!err.empty()) die(err);
-        for (int i = 0; i < n; i++) {
-            fwrite(t1[i].data(), 1, t1[i].size(), f1);
-            if (pe) fwrite(t2[i].data(), 1, t2[i].size(), f2);
-        }
-    }
-    fclose(f1);
-    if (f2) fclose(f2);
-    sq_destroy(c);
+            if (writer.joinable()) writer.join();
+            sq_destroy(c);
+        });
+    for (auto &t : gpus) t.join();
+    ::close(fd1);
+    if (fd2 >= 0) ::close(fd2);
+    if (!failure.empty()) die(failure);
+    if (o.verbose)
+        fprintf(stderr, "blocks %zu  gpus %d  %.2f s\n", nb, ndev, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     return 0;
 }
 
@@ -371,7 +539,12 @@ int main(int argc, char **argv) {
         else if (a == "-2") o.in2 = val();
         else if (a == "-o") o.out = val();
         else if (a == "-l") { o.lossy = true; o.lossy_r = atof(val().c_str()); }
-        else if (a == "-g") o.device = atoi(val().c_str());
+        else if (a == "-g") {                           // -g 0,2,3: the GPUs to shard the job over (default: all)
+            std::string v = val();
+            for (size_t p0 = 0; p0 <= v.size();) { size_t p1 = v.find(',', p0); if (p1 == std::string::npos) p1 = v.size(); if (p1 > p0) o.devices.push_back(atoi(v.substr(p0, p1 - p0).c_str())); p0 = p1 + 1; }
+        }
+        else if (a == "--usemodel") o.force_usemodel = atoi(val().c_str());
+        else if (a == "--parse-only") o.parse_only = true;
         else if (a == "-b") o.batch = atoi(val().c_str());
         else if (a == "-h") { printf("usage: seqarc_b200 -c [ref.fa] -1 a.fq [-2 b.fq] -o out [-l r] [-n] [-f]   (or: -c [ref.fa] a.fq [b.fq] out)\n       seqarc_b200 -d [ref.fa] in.arc -o out [-f]                            (or: -d [ref.fa] in.arc out)\n"); return 0; }
         else if (a[0] != '-') pos.push_back(a);
@@ -401,14 +574,14 @@ int main(int argc, char **argv) {
         if (k < pos.size() && o.out.empty()) o.out = pos[k++];
         if (k < pos.size()) die("unexpected argument " + pos[k]);
     }
-    if (getenv("SQ_CLI_PARSE_ONLY")) {             // argument handling is testable without a GPU
+    if (o.parse_only) {                            // argument handling is testable without a GPU
         printf("mode=%s ref=%s in1=%s in2=%s arc=%s out=%s lossy=%d md5=%d\n", o.compress ? "c" : o.decompress ? "d" : "-", o.ref.c_str(),
                o.in1.c_str(), o.in2.c_str(), o.arc.c_str(), o.out.c_str(), (int)o.lossy, (int)o.md5);
         return 0;
     }
     try {
         if (o.compress && !o.in1.empty() && !o.out.empty()) return do_compress(o);
-        if (o.decompress && !o.arc.empty() && !o.out.empty()) return do_decompress(o);
+        if (o.decompress && !o.arc.empty()) return do_decompress(o);
     } catch (const std::exception &e) {
         die(e.what());
     }

@@ -143,6 +143,11 @@ int  sq_last_wave_blocks(const sq_ctx *c);
  * 2 = name triples, 3 = number of coded symbols per stream (3 x u64). block = index in the wave. */
 int  sq_debug_fetch(sq_ctx *c, int what, int block, void *dst, uint64_t cap, uint64_t *got);
 
+/* number of CUDA devices this process can use (0 without a driver / device).  The host driver shards a job's blocks
+ * over them: one sq_ctx and one host thread per device, block records gathered in block order (the layout
+ * rule of addBlockPEInfo @0x412f30: offset = previous offset + previous length). */
+int  sq_device_count(void);
+
 const char *sq_version(void);
 
 #ifdef __cplusplus

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 CLI = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
 
 # every golden archive, rule-predictable IDs (ERR / SRR style) included: byte identity expected
-IDENTICAL = ["err_pe1000", "err_pe1000_nomd5", "srr_pe100", "illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
+IDENTICAL = ["illumina_pe_trim_blocks", "err_pe1000", "err_pe1000_nomd5", "srr_pe100", "illumina_pe150", "illumina_pe150_n", "illumina_pe150_3blocks", "illumina_pe150_lossy", "illumina_pe150_q1",
              "illumina_pe150_q3s2", "se100_q8", "se100_q8_3blocks", "se100_q8_usemodel", "illumina_pe150_usemodel",
              # BASELINE configs[4]: reference index given, nothing maps
              "illumina_pe150_ref", "se100_q8_ref", "err_pe1000_ref", "illumina_pe150_ref_3blocks",
@@ -53,12 +53,12 @@ def _setup(name, d):
     return m, fq, paths
 
 
-def _compress(m, paths, d, out="out"):
+def _compress(m, paths, d, out="out", extra=()):
     args = [CLI, "-c", "-f"] + (["ref.fa"] if m.get("ref") else []) + ["-1", paths[0]] + (["-2", paths[1]] if m["pe"] else []) + ["-o", out] + m["opts"]
-    env = dict(os.environ)
     if m.get("usemodel"):
-        env["SQ_FORCE_USEMODEL"] = "1"       # the golden was made with the size-faking shim
-    r = subprocess.run(args, cwd=d, env=env, capture_output=True, text=True, timeout=600)
+        args += ["--usemodel", "1"]          # the golden was made with the size-faking shim
+    args += list(extra)
+    r = subprocess.run(args, cwd=d, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     return open(os.path.join(d, out + ".arc"), "rb").read()
 
@@ -144,3 +144,60 @@ def test_config1_reference_test_pair_matches_survey_md5():
                 assert r.returncode == 0, r.stderr
                 assert open(os.path.join(d, "back_1.fastq"), "rb").read() == texts[0]
                 assert open(os.path.join(d, "back_2.fastq"), "rb").read() == texts[1]
+
+
+def _ngpu():
+    import fastqueeze_b200
+    return int(fastqueeze_b200.lib().sq_device_count())
+
+
+@pytest.mark.parametrize("name", ["illumina_pe150_3blocks", "se100_q8_3blocks", "illumina_pe_trim_blocks"])
+def test_cli_small_batches_keep_block_order(name):
+    """One block per GPU call (-b 1): the batches go through the reader -> GPU -> ordered-writer pipeline one after
+    the other and the archive is still the reference's -t 1 archive, block for block."""
+    with tempfile.TemporaryDirectory() as d:
+        m, fq, paths = _setup(name, d)
+        arc = _compress(m, paths, d, extra=["-b", "1"])
+        assert hashlib.md5(arc).hexdigest() == m["arc_md5"]
+        r = subprocess.run([CLI, "-d", "-f", "out.arc", "-o", "back", "-b", "1"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs = ["back_1.fastq", "back_2.fastq"] if m["pe"] else ["back.fastq"]
+        for o, t in zip(outs, fq):
+            assert open(os.path.join(d, o), "rb").read() == t
+
+
+@pytest.mark.parametrize("ng", [2, 4, 8])
+@pytest.mark.parametrize("name", ["illumina_pe150_3blocks", "illumina_pe_trim_blocks", "se100_q8_usemodel"])
+def test_cli_sharded_over_gpus_is_byte_identical(name, ng):
+    """The job sharded over ng GPUs (one host thread + one context per GPU, batches of one block dealt out, records
+    gathered in block order): the archive is byte-identical to SeqArc-1.6 -t 1, and the sharded decode restores the input."""
+    if _ngpu() < ng:
+        pytest.skip("needs %d GPUs" % ng)
+    with tempfile.TemporaryDirectory() as d:
+        m, fq, paths = _setup(name, d)
+        devs = ",".join(str(i) for i in range(ng))
+        arc = _compress(m, paths, d, extra=["-g", devs, "-b", "1"])
+        if m.get("usemodel"):
+            want = common.case_archive(name)
+            assert arc == want
+        else:
+            assert hashlib.md5(arc).hexdigest() == m["arc_md5"]
+        r = subprocess.run([CLI, "-d", "-f", "out.arc", "-o", "back", "-g", devs], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs = ["back_1.fastq", "back_2.fastq"] if m["pe"] else ["back.fastq"]
+        for o, t in zip(outs, fq):
+            assert open(os.path.join(d, o), "rb").read() == t
+
+
+def test_cli_decompress_without_prefix_reuses_input_names():
+    """README.md:97: without a prefix the outputs are named exactly like the compression inputs (measured with the
+    reference: `SeqArc -d x.arc` writes a_1.fq / a_2.fq into the current directory)."""
+    with tempfile.TemporaryDirectory() as d:
+        m, fq, paths = _setup("err_pe1000", d)
+        _compress(m, paths, d)
+        sub = os.path.join(d, "sub")
+        os.mkdir(sub)
+        r = subprocess.run([CLI, "-d", "../out.arc"], cwd=sub, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        for p, t in zip(paths, fq):
+            assert open(os.path.join(sub, os.path.basename(p)), "rb").read() == t

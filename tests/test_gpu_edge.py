@@ -126,10 +126,14 @@ def test_input_the_reference_cannot_represent_is_rejected(fq):
     good = ragged_block(7, 300)
     long_id = po.block_from_records([(b"x" * 300, b"ACGT", b"IIII")])
     bad_q = po.block_from_records([(b"q", b"ACGT", b"II\x1fI")])
-    mbs = [common.to_membuf(b) for b in (good, long_id, bad_q)]
+    del_q = po.block_from_records([(b"q", b"ACGT", b"II\x7fI")])                 # 0x7f would become symbol 94, the read terminator
+    hi_id = po.block_from_records([(b"id\xc3\xa9 1", b"ACGT", b"IIII")])           # the name model codes ch & 0x7f
+    tilde = po.block_from_records([(b"q", b"ACGT", b"I~~I")])                     # '~' (symbol 93) is the largest quality the coder holds
+    mbs = [common.to_membuf(b) for b in (good, long_id, bad_q, del_q, hi_id, tilde)]
     codec.doFqzEncode(mbs, raise_on_error=False)
     assert mbs[0].status == 0 and mbs[0].out == po.Oracle().encode_block(good)      # a bad block does not hurt its neighbours
-    assert mbs[1].status == -5 and mbs[2].status == -5                              # SQ_ERR_INPUT
+    assert [m.status for m in mbs[1:5]] == [-5, -5, -5, -5]                          # SQ_ERR_INPUT
+    assert mbs[5].status == 0 and mbs[5].out == po.Oracle().encode_block(tilde)
     codec.close()
 
 

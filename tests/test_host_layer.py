@@ -209,10 +209,9 @@ def test_cli_argument_forms():
     """Both forms of the reference command line: -1 / -2 / -o, or positional [ref.fa] inputs prefix."""
     import subprocess
     cli = os.path.join(common.ROOT, "fastqueeze_b200", "seqarc_b200")
-    env = dict(os.environ, SQ_CLI_PARSE_ONLY="1")
 
     def parse(args):
-        out = subprocess.run([cli] + args.split(), env=env, capture_output=True, text=True, cwd=tempfile.gettempdir())
+        out = subprocess.run([cli, "--parse-only"] + args.split(), capture_output=True, text=True, cwd=tempfile.gettempdir())
         assert out.returncode == 0, out.stderr
         return dict(kv.split("=", 1) for kv in out.stdout.split())
 
