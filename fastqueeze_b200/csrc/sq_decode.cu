@@ -625,9 +625,17 @@ SQ_D u32 q4_pstep(uint4 &M, u32 &last, QPend &P, RcWin &rc, uint4 *tab, u8 *qp, 
         M.x += addx;
         M.y += addy;
         M.w = (M.w & 0xf0ffffffu) | ((M.w + (1u << 24)) & (15u << 24));
-        if (tot + 8 > 0xffe0u) q4_halve(M, lane);
-        if (bubdue) q4_bubble(M, kl, (p1 ? 1 : 0) + (p2 ? 1 : 0), lane);
-        M.z = recip32(M.y >> 16);
+        if (special || bubdue) {
+            if (tot + 8 > 0xffe0u) q4_halve(M, lane);
+            if (bubdue) q4_bubble(M, kl, (p1 ? 1 : 0) + (p2 ? 1 : 0), lane);
+            M.z = recip32(M.y >> 16);
+        } else {                                      // the same context again (runs of one quality value): Newton refresh as in q4_apply
+            const u32 d = M.y >> 16;
+            u32 e = M.z;
+            e -= __umulhi(e, e * d);
+            if ((i32)(e * d) >= 0) e--;
+            M.z = e;
+        }
         q4_st(tab + (u64)last * 32, M);
         if (nl != last) M = Mn;
         q4_pend_none(P, dummy_ctx);

@@ -783,8 +783,6 @@ struct RbSmem {
     u8 g[128 * 128];             // fill value of the ordered pair (lo, hi)
     u32 ok[128 * 128 / 32];      // bit (lo * 128 + hi)
     u32 tile[RB_TILE / 4];
-    u64 patch_start;
-    u32 patch_v;
 };
 __global__ void __launch_bounds__(32) k_rblock(const BlockDesc *bd, int B, double r) {
     __shared__ RbSmem sm;
@@ -809,44 +807,49 @@ __global__ void __launch_bounds__(32) k_rblock(const BlockDesc *bd, int B, doubl
     }
     __syncwarp();
     u8 *tb = (u8 *)sm.tile;
-    // scan state (lane 0): the open run [start, i) with its min / max
+    // Scan state (warp-uniform): the open run [start, ...) with its min / max.  The 32 lanes test 32 bytes at a time
+    // against [mn, mx]; only the first byte outside the range is an event (extend the range, or close the run and
+    // open the next one with that byte), after which the scan resumes right behind it with the new range.  Bytes
+    // inside the range cost one ballot per 32, so the scan runs at the speed of its events, not of its bytes.
     u64 start = 0;
-    int mn = 0, mx = 0;
-    bool open = false;
+    int mn = q[0] & 127, mx = mn;
     for (u64 t0 = 0; t0 < n; t0 += RB_TILE) {
-        u32 tn = (u32)(n - t0 < RB_TILE ? n - t0 : RB_TILE);
+        const u32 tn = (u32)(n - t0 < RB_TILE ? n - t0 : RB_TILE);
         for (u32 k = lane; k < tn; k += 32) tb[k] = q[t0 + k];
         __syncwarp();
-        if (lane == 0) {
-            sm.patch_start = ~0ull;
-            for (u32 k = 0; k < tn; k++) {
-                int ch = tb[k] & 127;
-                if (!open) { open = true; start = t0 + k; mn = mx = ch; continue; }
-                if (ch >= mn && ch <= mx) continue;
-                if (ch > mx) { int idx = mn * 128 + ch; if ((sm.ok[idx >> 5] >> (idx & 31)) & 1) { mx = ch; continue; } }
-                else { int idx = ch * 128 + mx; if ((sm.ok[idx >> 5] >> (idx & 31)) & 1) { mn = ch; continue; } }
-                // close [start, t0 + k): the part inside this tile now, an earlier part as a patch
-                u8 v = sm.g[mn * 128 + mx];
-                u32 from = start >= t0 ? (u32)(start - t0) : 0;
-                for (u32 j = from; j < k; j++) tb[j] = v;
-                if (start < t0) { sm.patch_start = start; sm.patch_v = v; }
-                start = t0 + k; mn = mx = ch;
-            }
-            if (t0 + tn >= n && open) {                      // end of data closes the last run
-                u8 v = sm.g[mn * 128 + mx];
-                u32 from = start >= t0 ? (u32)(start - t0) : 0;
-                for (u32 j = from; j < tn; j++) tb[j] = v;
-                if (start < t0) { sm.patch_start = start; sm.patch_v = v; }
-                start = n;
-            }
+        u32 p = t0 == 0 ? 1u : 0u;                            // byte 0 opened the first run
+        while (p < tn) {
+            const u32 i = p + lane;
+            const int ch = i < tn ? (tb[i] & 127) : mn;       // bytes past the tile never trigger
+            const u32 m = __ballot_sync(FULL, ch < mn || ch > mx);
+            if (m == 0) { p += 32; continue; }
+            const int j = __ffs(m) - 1;
+            const int c = __shfl_sync(FULL, ch, j);
+            const u32 e = p + (u32)j;
+            p = e + 1;
+            if (c > mx) { const int idx = mn * 128 + c; if ((sm.ok[idx >> 5] >> (idx & 31)) & 1) { mx = c; continue; } }
+            else { const int idx = c * 128 + mx; if ((sm.ok[idx >> 5] >> (idx & 31)) & 1) { mn = c; continue; } }
+            // close [start, t0 + e): the part inside this tile in shared memory, an earlier part straight in global memory
+            const u8 v = sm.g[mn * 128 + mx];
+            const u32 from = start >= t0 ? (u32)(start - t0) : 0;
+            __syncwarp();
+            for (u32 x = from + lane; x < e; x += 32) tb[x] = v;
+            if (start < t0) for (u64 x = start + lane; x < t0; x += 32) q[x] = v;
+            __syncwarp();
+            start = t0 + e; mn = mx = c;
         }
-        __syncwarp();
-        // at most one run reaches into a tile from the left, so one patch per tile
-        u64 ps = sm.patch_start;
-        if (ps != ~0ull) { u8 v = (u8)sm.patch_v; for (u64 j = ps + lane; j < t0; j += 32) q[j] = v; }
+        if (t0 + tn >= n) {                                   // end of data closes the last run
+            const u8 v = sm.g[mn * 128 + mx];
+            const u32 from = start >= t0 ? (u32)(start - t0) : 0;
+            __syncwarp();
+            for (u32 x = from + lane; x < tn; x += 32) tb[x] = v;
+            if (start < t0) for (u64 x = start + lane; x < t0; x += 32) q[x] = v;
+            __syncwarp();
+            start = n;
+        }
         // write back what is final: everything before the run that is still open
-        u64 os = __shfl_sync(0xffffffffu, start, 0);
-        u32 fin = os >= t0 + tn ? tn : (os > t0 ? (u32)(os - t0) : 0);
+        const u32 fin = start >= t0 + tn ? tn : (start > t0 ? (u32)(start - t0) : 0);
+        __syncwarp();
         for (u32 k = lane; k < fin; k += 32) q[t0 + k] = tb[k];
         __syncwarp();
     }
