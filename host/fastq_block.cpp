@@ -124,8 +124,16 @@ bool BlockReader::next_text(std::vector<char> &t1, std::vector<char> &t2) {
     // cultPEbuf @0x432180 (cut = true): newline positions of both buffers, back off two lines from the
     // shorter one, find the record start in file 1, cut file 2 after the same number of lines
     std::vector<int> nl[2];
-    for (int k = 0; k < 2; k++)
-        for (size_t i = 0; i < t[k]->size(); i++) if ((*t[k])[i] == '\n') nl[k].push_back((int)i);
+    for (int k = 0; k < 2; k++) {                                    // memchr: this scan is on the single reader thread
+        const char *b0 = t[k]->data(), *end = b0 + t[k]->size();
+        nl[k].reserve(t[k]->size() / 64);
+        for (const char *p = b0; p < end;) {
+            const char *q = (const char *)memchr(p, '\n', (size_t)(end - p));
+            if (!q) break;
+            nl[k].push_back((int)(q - b0));
+            p = q + 1;
+        }
+    }
     int nmin = (int)std::min(nl[0].size(), nl[1].size());
     if (nmin < 3) throw std::runtime_error("block too small to cut a paired-end buffer");
     int e = nmin - 2;
@@ -206,23 +214,31 @@ bool BlockReader::next(MemBuf &mb) {
     return true;
 }
 
-void render_block(const MemBuf &mb, bool pe, std::string &o1, std::string &o2) {
+void render_raw(const uint8_t *ids, const uint16_t *idlen, const uint8_t *seq, const uint8_t *qual, const int32_t *seqlen,
+                uint32_t nreads, bool comment, bool pe, std::string &o1, std::string &o2) {
     o1.clear(); o2.clear();
+    size_t tot[2] = {0, 0};
+    for (uint32_t r = 0; r < nreads; r++) tot[(pe && (r & 1)) ? 1 : 0] += (size_t)idlen[r] * (comment ? 2 : 1) + 2 * (size_t)seqlen[r] + 6;
+    o1.reserve(tot[0]); o2.reserve(tot[1]);
     size_t io = 0, so = 0;
-    for (uint32_t r = 0; r < mb.nreads(); r++) {
+    for (uint32_t r = 0; r < nreads; r++) {
         std::string &o = (pe && (r & 1)) ? o2 : o1;
         o.push_back('@');
-        o.append((const char *)mb.ids.data() + io, mb.idlen[r]);
+        o.append((const char *)ids + io, idlen[r]);
         o.push_back('\n');
-        o.append((const char *)mb.seq.data() + so, mb.seqlen[r]);
+        o.append((const char *)seq + so, seqlen[r]);
         o.append("\n+");
-        if (mb.comment) o.append((const char *)mb.ids.data() + io, mb.idlen[r]);
+        if (comment) o.append((const char *)ids + io, idlen[r]);
         o.push_back('\n');
-        o.append((const char *)mb.qual.data() + so, mb.seqlen[r]);
+        o.append((const char *)qual + so, seqlen[r]);
         o.push_back('\n');
-        io += mb.idlen[r];
-        so += mb.seqlen[r];
+        io += idlen[r];
+        so += seqlen[r];
     }
+}
+
+void render_block(const MemBuf &mb, bool pe, std::string &o1, std::string &o2) {
+    render_raw(mb.ids.data(), mb.idlen.data(), mb.seq.data(), mb.qual.data(), mb.seqlen.data(), mb.nreads(), mb.comment, pe, o1, o2);
 }
 
 }  // namespace sqhost

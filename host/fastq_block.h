@@ -79,5 +79,7 @@ private:
 void parse_block(const std::vector<char> &t1, const std::vector<char> &t2, bool pe, MemBuf &mb);
 // inverse (recoverDataNoComment): MemBuf -> FASTQ text, PE de-interleaved
 void render_block(const MemBuf &mb, bool pe, std::string &o1, std::string &o2);
+void render_raw(const uint8_t *ids, const uint16_t *idlen, const uint8_t *seq, const uint8_t *qual, const int32_t *seqlen,
+                uint32_t nreads, bool comment, bool pe, std::string &o1, std::string &o2);
 
 }  // namespace sqhost

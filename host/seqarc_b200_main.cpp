@@ -15,6 +15,7 @@
 #include <fcntl.h>
 #include <future>
 #include <map>
+#include <memory>
 #include <unistd.h>
 #include <mutex>
 #include <thread>
@@ -216,8 +217,9 @@ static int do_compress(const Opt &o) {
     // Blocks per GPU call.  The chain kernels take the same time for one block as for a wave of them, so a batch
     // should be this GPU's whole share of the job when the workspace holds it (~0.75 GB per default-size block).
     uint64_t est_blocks = std::max<uint64_t>(1, ((gz ? total * 4 : total) + ((uint64_t)o.block_mb << 20) - 1) / ((uint64_t)o.block_mb << 20));
-    uint64_t cap_blocks = std::max<uint64_t>(1, (uint64_t)(100.0 * 50 / std::max(1, o.block_mb)));
-    int batch = o.batch > 0 ? o.batch : (int)std::min<uint64_t>(cap_blocks, (est_blocks + ndev - 1) / ndev);
+    uint64_t cap_blocks = std::max<uint64_t>(1, (uint64_t)(140.0 * 50 / std::max(1, o.block_mb)));
+    uint64_t share = (est_blocks + ndev - 1) / ndev, rounds = (share + cap_blocks - 1) / cap_blocks;
+    int batch = o.batch > 0 ? o.batch : (int)((share + rounds - 1) / rounds);       // equal batches: 274 blocks on one GPU = 2 x 137
     auto t0 = std::chrono::steady_clock::now();
 
     // reader: cuts block texts sequentially, a pool parses them into MemBufs, batches go to whichever GPU is free
@@ -446,20 +448,27 @@ static int do_decompress(const Opt &o) {
             std::thread writer;                        // renders / writes batch k while the GPU decodes batch k + 1
             for (size_t b0 = lo; b0 < hi && failure.empty(); b0 += batch) {
                 int n = (int)std::min<size_t>(batch, hi - b0);
+                // output buffers of the batch: uninitialised storage (a zero-filled std::vector would touch every byte twice)
+                struct Out {
+                    std::unique_ptr<uint8_t[]> ids, seq, qual;
+                    std::unique_ptr<uint16_t[]> idlen;
+                    std::unique_ptr<int32_t[]> seqlen;
+                };
                 auto recs = std::make_shared<std::vector<const uint8_t *>>(n);
                 auto lens = std::make_shared<std::vector<uint64_t>>(n);
                 auto dec = std::make_shared<std::vector<sq_block_dec>>(n);
-                auto mbs = std::make_shared<std::vector<MemBuf>>(n);
+                auto bufs = std::make_shared<std::vector<Out>>(n);
                 for (int i = 0; i < n; i++) {
                     const BlockIndex &bi = ar.idx[b0 + i];
                     (*recs)[i] = ar.base + bi.arc_off;
                     (*lens)[i] = bi.len;
                     uint64_t src = (uint64_t)bi.src_bytes[0] + bi.src_bytes[1];
-                    MemBuf &m = (*mbs)[i];
-                    m.ids.resize(src + 64); m.seq.resize(src / 2 + 64); m.qual.resize(src / 2 + 64);
+                    uint64_t idcap = src + 64, scap = src / 2 + 64;           // a record is "@id\n seq\n +\n qual\n": ids < src, seq = qual < src / 2
                     uint32_t rcap = (uint32_t)(src / 6 + 16);
-                    m.idlen.resize(rcap); m.seqlen.resize(rcap);
-                    (*dec)[i] = {m.ids.data(), m.ids.size(), m.seq.data(), m.qual.data(), m.seq.size(), m.idlen.data(), m.seqlen.data(), rcap, 0, 0, 0, 0,
+                    Out &u = (*bufs)[i];
+                    u.ids.reset(new uint8_t[idcap]); u.seq.reset(new uint8_t[scap]); u.qual.reset(new uint8_t[scap]);
+                    u.idlen.reset(new uint16_t[rcap]); u.seqlen.reset(new int32_t[rcap]);
+                    (*dec)[i] = {u.ids.get(), idcap, u.seq.get(), u.qual.get(), scap, u.idlen.get(), u.seqlen.get(), rcap, 0, 0, 0, 0,
                                  bi.longflag ? 1 : 0};
                 }
                 int rc = sq_decode_blocks(c, recs->data(), lens->data(), n, dec->data());
@@ -469,39 +478,41 @@ static int do_decompress(const Opt &o) {
                     break;
                 }
                 if (writer.joinable()) writer.join();
-                writer = std::thread([&, recs, lens, dec, mbs, b0, n]() {
+                writer = std::thread([&, recs, lens, dec, bufs, b0, n]() {
                     // regenerate rule-based IDs, render the FASTQ text of the batch's blocks in parallel, write at the recorded offsets
                     std::atomic<int> next{0};
                     auto work = [&]() {
                         std::string t1, t2;
+                        std::vector<uint8_t> rids;
+                        std::vector<uint16_t> ridl;
                         for (int i; (i = next.fetch_add(1)) < n;) {
-                            MemBuf &m = (*mbs)[i];
+                            Out &u = (*bufs)[i];
                             const sq_block_dec &dd = (*dec)[i];
-                            m.idlen.resize(dd.nreads); m.seqlen.resize(dd.nreads);
+                            const uint8_t *ids = u.ids.get();
+                            const uint16_t *idl = u.idlen.get();
                             const char *bad = nullptr;
                             if (rule) {               // IDProcess::decodeIDS @0x430610: regenerate the IDs from the block's first ID
                                 const uint8_t *pay = nullptr, *md5 = nullptr;
                                 size_t plen = 0;
                                 if (!find_id_payload((*recs)[i], (*lens)[i], ar.p.md5, &pay, &plen, &md5)) bad = "decode: block without an ID stream";
                                 else {
-                                    m.ids.clear(); m.idlen.clear();
-                                    if (!decode_ids(pay, plen, ar.p.idbin, m.seqlen.data(), dd.nreads, m.ids, m.idlen)) bad = "decode: bad rule-based ID record";
+                                    rids.clear(); ridl.clear();
+                                    if (!decode_ids(pay, plen, ar.p.idbin, u.seqlen.get(), dd.nreads, rids, ridl)) bad = "decode: bad rule-based ID record";
                                     else if (md5) {
                                         uint8_t dig[16];
-                                        md5_digest(m.ids.data(), m.ids.size(), dig);
+                                        md5_digest(rids.data(), rids.size(), dig);
                                         if (memcmp(dig, md5, 16) != 0) bad = "decode: Name md5 unequal";
                                     }
+                                    ids = rids.data(); idl = ridl.data();
                                 }
-                            } else m.ids.resize(dd.idbytes);
+                            }
                             if (bad) { fail(bad); continue; }
-                            m.seq.resize(dd.seqbytes); m.qual.resize(dd.seqbytes);
-                            m.comment = ar.p.comment;
-                            render_block(m, pe, t1, t2);
+                            render_raw(ids, idl, u.seq.get(), u.qual.get(), u.seqlen.get(), dd.nreads, ar.p.comment, pe, t1, t2);
                             const BlockIndex &bi = ar.idx[b0 + i];
                             if (t1.size() != bi.src_bytes[0] || (pe && t2.size() != bi.src_bytes[1])) { fail("decode len is not equal org len"); continue; }
                             pwrite_all(fd1, t1, bi.src_off[0]);
                             if (pe) pwrite_all(fd2, t2, bi.src_off[1]);
-                            MemBuf().ids.swap(m.ids); MemBuf().seq.swap(m.seq); MemBuf().qual.swap(m.qual);
+                            u = Out();
                         }
                     };
                     unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)n}));
