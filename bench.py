@@ -476,11 +476,13 @@ def main():
     def measure(block_ids, steps, warmup, label):
         """Build the rank's share, run warmup + timed steps; returns (workload, max-over-ranks ms, clocks)."""
         t0 = time.perf_counter()
-        h = make_ctx(L_, _lib, local, stream, cfg, usemodel)
+        # the workload's tensors first: the context then takes its workspace out of what is left of the HBM
+        w = Workload(torch, L_, _lib, None, stream, dev, shape, cfg, block_ids, units)
+        h = w.h = make_ctx(L_, _lib, local, stream, cfg, usemodel)
         if usemodel:
             nbytes, npairs = train_snapshot(torch, L_, _lib, h, dev, shape, units)
+            torch.cuda.empty_cache()
             log("rank %d: trained the %d-byte model snapshot on %d %s (pre-process, untimed)" % (rank, nbytes, npairs, "pairs" if shape.pe else "reads"))
-        w = Workload(torch, L_, _lib, h, stream, dev, shape, cfg, block_ids, units)
         log("rank %d: %s: %d blocks (%.1f MB FASTQ) ready in %.1fs" % (rank, label, w.n, w.fastq_bytes / 1e6, time.perf_counter() - t0))
         for _ in range(warmup):
             w.step_device()

@@ -247,6 +247,7 @@ struct WaveAcc {
         t += 16 * me + 512;                                   // elemA + elemB
         t += 8 * ms + 256;                                    // seglist
         t += (u64)B * (1u << SQ_SORT_BITS_WIDE) * mt * 4 + 256;    // hist
+        t += (u64)B * (((u64)(1u << SQ_SORT_BITS_WIDE) * mt + 4095) / 4096 + 1) * 4 + 512;    // its scan's chunk sums
         t += (u64)B * (sizeof(BlockDesc) + sizeof(BlockState) + 6 * 4 + 8 + 4) + 2048;
         (void)c;
         return t;
@@ -334,6 +335,7 @@ int encode_wave(sq_ctx *c, const sq_block_in *blocks, int n, sq_block_out *out, 
     u64 maxtiles = 0;
     for (int s = 0; s < ST_COUNT; s++) maxtiles = std::max(maxtiles, (w.maxbound[s] + SQ_TILE - 1) / SQ_TILE);
     w.hist = (u32 *)need(take<u32>(A, (u64)n * (1u << SQ_SORT_BITS_WIDE) * maxtiles + 1));
+    w.scanpart = (u32 *)need(take<u32>(A, (u64)n * (((u64)(1u << SQ_SORT_BITS_WIDE) * maxtiles + 4095) / 4096 + 1) + 1));
     u64 segcap = std::max(segsum[0], std::max(segsum[1], segsum[2])) + 1;
     if (segcap > 0xffffffffull) { c->err = "segment list too large"; return SQ_ERR_ARG; }
     w.segcap = (u32)segcap;

@@ -283,95 +283,200 @@ __global__ void k_set_counts(BlockState *bs, const u32 *totals, int B, int with_
 }
 
 // =============================================================================================
-// 2. stable LSD radix sort by context key, segmented per block.  One warp owns one tile of
-// SQ_TILE consecutive elements; digit ranks come from __match_any_sync so any key skew costs the same.
+// 2. stable LSD radix sort by context key, segmented per block (BlockDesc::ebase / BlockState::nsym).
+// One CTA of 512 threads owns one tile of SQ_TILE = 8192 consecutive elements.  A pass is
+//   k_sort_hist     per-tile digit counts                           -> hist[block][digit][tile]
+//   k_scan_*        exclusive scan of each block's [digit][tile] table (three small parallel kernels)
+//   k_sort_scatter  the tile is ranked (warp: __match_any_sync, so key skew costs nothing; CTA: per-warp counters
+//                   scanned per digit), written to SHARED memory in sorted order, and copied out from there:
+//                   consecutive threads write consecutive elements of one digit's run, so the global stores are
+//                   coalesced runs (8 elements = 64 B on average for 10-bit digits of the uniformly distributed
+//                   base contexts, 32 elements for 8-bit digits) instead of one 8-byte store per sector.
 // hist layout per block: [digit][tile] (tile-minor), block stride = D * maxtiles.
+#define SQ_SORT_WARPS (SQ_SORT_THREADS / 32)
+#define SQ_SORT_ITEMS (SQ_TILE / SQ_SORT_THREADS)            // elements per thread (16)
+static_assert(SQ_TILE == SQ_SORT_THREADS * SQ_SORT_ITEMS && SQ_SORT_ITEMS == 16, "tile shape");
+
 template <int BITS>
 __global__ void __launch_bounds__(SQ_SORT_THREADS) k_sort_hist(const u64 *src, u32 *hist, const BlockDesc *bd,
                                                                const BlockState *bs, int stream, int shift, u32 maxtiles) {
     constexpr int D = 1 << BITS;
-    extern __shared__ u32 smem[];
-    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    u32 *cnt = smem + wid * D;
-    int b = blockIdx.y;
-    u32 tile = blockIdx.x * (SQ_SORT_THREADS / 32) + wid;
-    if (tile >= maxtiles) return;
-    for (int d = lane; d < D; d += 32) cnt[d] = 0;
-    __syncwarp();
-    u32 n = bs[b].nsym[stream];
-    u64 t0 = (u64)tile * SQ_TILE;
+    __shared__ u32 cnt[D];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const u32 tile = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += SQ_SORT_THREADS) cnt[d] = 0;
+    __syncthreads();
+    const u32 n = bs[b].nsym[stream];
+    const u64 t0 = (u64)tile * SQ_TILE;
     if (t0 < n) {
-        u32 m = (u32)min((u64)SQ_TILE, (u64)n - t0);
+        const u32 m = (u32)min((u64)SQ_TILE, (u64)n - t0);
         const u64 *p = src + bd[b].ebase[stream] + t0;
-        for (u32 i0 = 0; i0 < m; i0 += 32) {
-            u32 i = i0 + lane;
-            bool valid = i < m;
-            u32 act = __ballot_sync(FULL, valid);
+        const u32 lt = lanemask_lt();
+#pragma unroll 4
+        for (int it = 0; it < SQ_SORT_ITEMS; it++) {
+            const u32 i = (u32)wid * (SQ_TILE / SQ_SORT_WARPS) + it * 32 + lane;
+            const bool valid = i < m;
+            const u32 act = __ballot_sync(FULL, valid);
             if (valid) {
-                u32 dg = (u32)(p[i] >> (40 + shift)) & (D - 1);
-                u32 peers = __match_any_sync(act, dg);
-                if ((peers & lanemask_lt()) == 0) cnt[dg] += __popc(peers);
+                const u32 dg = (u32)(p[i] >> (40 + shift)) & (D - 1);
+                const u32 peers = __match_any_sync(act, dg);
+                if ((peers & lt) == 0) atomicAdd(&cnt[dg], (u32)__popc(peers));
             }
-            __syncwarp();
         }
     }
+    __syncthreads();
     u32 *h = hist + (u64)b * D * maxtiles + tile;
-    for (int d = lane; d < D; d += 32) h[(u64)d * maxtiles] = cnt[d];
+    for (int d = threadIdx.x; d < D; d += SQ_SORT_THREADS) h[(u64)d * maxtiles] = cnt[d];
 }
 
-// exclusive scan of one block's [digit][tile] histogram (grid.x = B)
-__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, u64 entries_per_block) {
-    __shared__ u32 wsum[32];
-    u32 *h = hist + (u64)blockIdx.x * entries_per_block;
-    u64 per = (entries_per_block + 1023) / 1024;
-    u64 lo = min(entries_per_block, (u64)threadIdx.x * per), hi = min(entries_per_block, lo + per);
+// exclusive scan of every block's [digit][tile] table, entries_per_block values each, in chunks of SQ_SCAN_CHUNK
+#define SQ_SCAN_CHUNK 4096
+__global__ void __launch_bounds__(256) k_scan_partial(const u32 *hist, u64 entries_per_block, u32 nchunks, u32 *part) {
+    __shared__ u32 ws[8];
+    const u32 *h = hist + (u64)blockIdx.y * entries_per_block;
+    const u64 lo = (u64)blockIdx.x * SQ_SCAN_CHUNK;
     u32 s = 0;
-    for (u64 i = lo; i < hi; i++) s += h[i];
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    u32 inc = warp_incl_scan(s, lane);
+    for (int k = 0; k < SQ_SCAN_CHUNK / 256; k++) { u64 i = lo + (u64)k * 256 + threadIdx.x; if (i < entries_per_block) s += h[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { u32 t = 0; for (int k = 0; k < 8; k++) t += ws[k]; part[(u64)blockIdx.y * nchunks + blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_scan_mid(u32 *part, u32 nchunks) {
+    __shared__ u32 wsum[32];
+    __shared__ u32 carry;
+    u32 *p = part + (u64)blockIdx.x * nchunks;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < nchunks; base += 1024) {
+        const u32 i = base + threadIdx.x;
+        const u32 v = i < nchunks ? p[i] : 0;
+        const u32 inc = warp_incl_scan(v, lane);
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) { u32 t = wsum[lane]; u32 ti = warp_incl_scan(t, lane); wsum[lane] = ti - t; }
+        __syncthreads();
+        const u32 excl = carry + wsum[wid] + inc - v;
+        if (i < nchunks) p[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_scan_final(u32 *hist, u64 entries_per_block, u32 nchunks, const u32 *part) {
+    __shared__ u32 wsum[8];
+    u32 *h = hist + (u64)blockIdx.y * entries_per_block;
+    const u64 lo = (u64)blockIdx.x * SQ_SCAN_CHUNK + (u64)threadIdx.x * (SQ_SCAN_CHUNK / 256);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 v[SQ_SCAN_CHUNK / 256], s = 0;
+#pragma unroll
+    for (int k = 0; k < SQ_SCAN_CHUNK / 256; k++) { v[k] = lo + k < entries_per_block ? h[lo + k] : 0; s += v[k]; }
+    const u32 inc = warp_incl_scan(s, lane);
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
-    if (wid == 0) { u32 t = wsum[lane]; u32 ti = warp_incl_scan(t, lane); wsum[lane] = ti - t; }
-    __syncthreads();
-    u32 run = wsum[wid] + inc - s;
-    for (u64 i = lo; i < hi; i++) { u32 t = h[i]; h[i] = run; run += t; }
+    u32 wbase = 0;
+    for (int k = 0; k < wid; k++) wbase += wsum[k];
+    u32 run = part[(u64)blockIdx.y * nchunks + blockIdx.x] + wbase + inc - s;
+#pragma unroll
+    for (int k = 0; k < SQ_SCAN_CHUNK / 256; k++) { if (lo + k < entries_per_block) h[lo + k] = run; run += v[k]; }
 }
 
 template <int BITS>
-__global__ void __launch_bounds__(SQ_SORT_THREADS) k_sort_scatter(const u64 *src, u64 *dst, const u32 *hist, const BlockDesc *bd,
-                                                                  const BlockState *bs, int stream, int shift, u32 maxtiles) {
+__global__ void __launch_bounds__(SQ_SORT_THREADS, 1) k_sort_scatter(const u64 *src, u64 *dst, const u32 *hist, const BlockDesc *bd,
+                                                                     const BlockState *bs, int stream, int shift, u32 maxtiles) {
     constexpr int D = 1 << BITS;
-    extern __shared__ u32 smem[];
-    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    u32 *cur = smem + wid * D;
-    int b = blockIdx.y;
-    u32 tile = blockIdx.x * (SQ_SORT_THREADS / 32) + wid;
-    if (tile >= maxtiles) return;
-    u32 n = bs[b].nsym[stream];
-    u64 t0 = (u64)tile * SQ_TILE;
+    extern __shared__ __align__(16) u8 smem_raw[];
+    u64 *sorted = (u64 *)smem_raw;                                   // [SQ_TILE]
+    u32 *ls = (u32 *)(sorted + SQ_TILE);                              // [D] tile-local start of each digit's run
+    u32 *gb = ls + D;                                                 // [D] where that run goes in the block's array
+    u16 *wcnt = (u16 *)(gb + D);                                      // [SQ_SORT_WARPS][D] per-warp counts -> per-warp bases
+    __shared__ u32 wsum[SQ_SORT_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const u32 tile = blockIdx.x;
+    const u32 n = bs[b].nsym[stream];
+    const u64 t0 = (u64)tile * SQ_TILE;
     if (t0 >= n) return;
-    const u32 *h = hist + (u64)b * D * maxtiles + tile;
-    for (int d = lane; d < D; d += 32) cur[d] = h[(u64)d * maxtiles];
-    __syncwarp();
-    u32 m = (u32)min((u64)SQ_TILE, (u64)n - t0);
+    const u32 m = (u32)min((u64)SQ_TILE, (u64)n - t0);
     const u64 *p = src + bd[b].ebase[stream] + t0;
     u64 *q = dst + bd[b].ebase[stream];
-    u32 lt = lanemask_lt();
-    for (u32 i0 = 0; i0 < m; i0 += 32) {
-        u32 i = i0 + lane;
-        bool valid = i < m;
-        u32 act = __ballot_sync(FULL, valid);
+    for (int d = threadIdx.x; d < D * SQ_SORT_WARPS / 2; d += SQ_SORT_THREADS) ((u32 *)wcnt)[d] = 0;
+    const u32 *h = hist + (u64)b * D * maxtiles + tile;
+    for (int d = threadIdx.x; d < D; d += SQ_SORT_THREADS) gb[d] = h[(u64)d * maxtiles];
+    __syncthreads();
+    // 1. rank inside the warp's 512 consecutive elements (stream order: iteration, then lane)
+    u64 e[SQ_SORT_ITEMS];
+    u16 rk[SQ_SORT_ITEMS];
+    u16 *mycnt = wcnt + wid * D;
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int it = 0; it < SQ_SORT_ITEMS; it++) {
+        const u32 i = (u32)wid * (SQ_TILE / SQ_SORT_WARPS) + it * 32 + lane;
+        e[it] = i < m ? p[i] : 0;
+    }
+#pragma unroll
+    for (int it = 0; it < SQ_SORT_ITEMS; it++) {
+        const u32 i = (u32)wid * (SQ_TILE / SQ_SORT_WARPS) + it * 32 + lane;
+        const bool valid = i < m;
+        const u32 act = __ballot_sync(FULL, valid);
+        rk[it] = 0;
         if (valid) {
-            u64 e = p[i];
-            u32 dg = (u32)(e >> (40 + shift)) & (D - 1);
-            u32 peers = __match_any_sync(act, dg);
-            u32 rk = __popc(peers & lt);
-            u32 off = cur[dg];
+            const u32 dg = (u32)(e[it] >> (40 + shift)) & (D - 1);
+            const u32 peers = __match_any_sync(act, dg);
+            const u32 r = __popc(peers & lt);
+            const u32 base = mycnt[dg];
             __syncwarp(act);
-            if (rk == 0) cur[dg] = off + __popc(peers);
-            q[off + rk] = e;
+            if (r == 0) mycnt[dg] = (u16)(base + __popc(peers));
+            rk[it] = (u16)(base + r);
         }
         __syncwarp();
+    }
+    __syncthreads();
+    // 2. per digit: exclusive prefix over the warps, tile total; then the exclusive scan of the totals over the digits
+    u32 mine[D / SQ_SORT_THREADS > 0 ? D / SQ_SORT_THREADS : 1];
+    u32 tsum = 0;
+    constexpr int DPT = D / SQ_SORT_THREADS > 0 ? D / SQ_SORT_THREADS : 1;      // digits per thread (2 for D = 1024; D = 256: threads < 256 take one)
+#pragma unroll
+    for (int k = 0; k < DPT; k++) {
+        const int d = threadIdx.x * DPT + k;
+        u32 acc = 0;
+        if (d < D) {
+            for (int w = 0; w < SQ_SORT_WARPS; w++) { u32 t = wcnt[w * D + d]; wcnt[w * D + d] = (u16)acc; acc += t; }
+        }
+        mine[k] = acc;
+        tsum += acc;
+    }
+    const u32 inc = warp_incl_scan(tsum, lane);
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    u32 wbase = 0;
+    for (int k = 0; k < wid; k++) wbase += wsum[k];
+    u32 run = wbase + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < DPT; k++) {
+        const int d = threadIdx.x * DPT + k;
+        if (d < D) ls[d] = run;
+        run += mine[k];
+    }
+    __syncthreads();
+    // 3. the tile in sorted order, in shared memory
+#pragma unroll
+    for (int it = 0; it < SQ_SORT_ITEMS; it++) {
+        const u32 i = (u32)wid * (SQ_TILE / SQ_SORT_WARPS) + it * 32 + lane;
+        if (i < m) {
+            const u32 dg = (u32)(e[it] >> (40 + shift)) & (D - 1);
+            sorted[ls[dg] + mycnt[dg] + rk[it]] = e[it];
+        }
+    }
+    __syncthreads();
+    // 4. out: position k of the sorted tile belongs to its digit's run at gb[digit] + (k - ls[digit])
+    for (u32 k = threadIdx.x; k < m; k += SQ_SORT_THREADS) {
+        const u64 x = sorted[k];
+        const u32 dg = (u32)(x >> (40 + shift)) & (D - 1);
+        q[gb[dg] + (k - ls[dg])] = x;
     }
 }
 
@@ -1211,16 +1316,21 @@ cudaError_t sqk_emit(const EncWave &w, int stream, u64 *elem, cudaStream_t st, u
 }
 
 template <int BITS>
+static size_t sort_scatter_smem() { return (size_t)SQ_TILE * 8 + (size_t)(1 << BITS) * 8 + (size_t)SQ_SORT_WARPS * (1 << BITS) * 2; }
+
+template <int BITS>
 static cudaError_t sort_pass(const EncWave &w, int stream, const u64 *src, u64 *dst, int shift, u32 maxtiles,
                              cudaStream_t st, u64 *launches) {
     constexpr int D = 1 << BITS;
-    const int WPC = SQ_SORT_THREADS / 32;
-    size_t smem = (size_t)WPC * D * sizeof(u32);
-    dim3 grid(cdiv(maxtiles, WPC), w.B);
-    k_sort_hist<BITS><<<grid, SQ_SORT_THREADS, smem, st>>>(src, w.hist, w.bd, w.bs, stream, shift, maxtiles);
-    k_sort_scan<<<w.B, 1024, 0, st>>>(w.hist, (u64)D * maxtiles);
-    k_sort_scatter<BITS><<<grid, SQ_SORT_THREADS, smem, st>>>(src, dst, w.hist, w.bd, w.bs, stream, shift, maxtiles);
-    *launches += 3;
+    dim3 grid(maxtiles, w.B);
+    const u64 entries = (u64)D * maxtiles;
+    const u32 nchunks = cdiv(entries, SQ_SCAN_CHUNK);
+    k_sort_hist<BITS><<<grid, SQ_SORT_THREADS, 0, st>>>(src, w.hist, w.bd, w.bs, stream, shift, maxtiles);
+    k_scan_partial<<<dim3(nchunks, w.B), 256, 0, st>>>(w.hist, entries, nchunks, w.scanpart);
+    k_scan_mid<<<w.B, 1024, 0, st>>>(w.scanpart, nchunks);
+    k_scan_final<<<dim3(nchunks, w.B), 256, 0, st>>>(w.hist, entries, nchunks, w.scanpart);
+    k_sort_scatter<BITS><<<grid, SQ_SORT_THREADS, sort_scatter_smem<BITS>(), st>>>(src, dst, w.hist, w.bd, w.bs, stream, shift, maxtiles);
+    *launches += 5;
     return cudaGetLastError();
 }
 
@@ -1309,13 +1419,7 @@ cudaError_t sqk_enc_attrs() {
     CK(cudaFuncSetAttribute(k_rc, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_RC));
     CK(cudaFuncSetAttribute(k_md5, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_SMALL));
     CK(cudaFuncSetAttribute(k_side, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_CHAIN_SMEM_SMALL));
-    CK(cudaFuncSetAttribute(k_sort_hist<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
-    CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS) * 4));
-    CK(cudaFuncSetAttribute(k_sort_hist<SQ_SORT_BITS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS_WIDE) * 4));
-    CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (SQ_SORT_THREADS / 32) * (1 << SQ_SORT_BITS_WIDE) * 4));
+    CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_scatter_smem<SQ_SORT_BITS>()));
+    CK(cudaFuncSetAttribute(k_sort_scatter<SQ_SORT_BITS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_scatter_smem<SQ_SORT_BITS_WIDE>()));
     return cudaSuccess;
 }

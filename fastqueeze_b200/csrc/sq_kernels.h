@@ -7,8 +7,8 @@
 #define SQ_ERR_INPUT_K (-5)
 #define SQ_ERR_FORMAT_K (-6)
 
-#define SQ_TILE 8192            // sort tile: elements owned by one warp
-#define SQ_SORT_THREADS 256
+#define SQ_TILE 8192            // sort tile: elements owned by one CTA
+#define SQ_SORT_THREADS 512
 #define SQ_SORT_BITS 8          // radix digit width
 #define SQ_SORT_BITS_WIDE 10    // ... for 17..20-bit keys (two passes)
 #define SQ_CHAIN_SMEM_RC (72 * 1024)      // dynamic shared memory requested only to cap chain CTAs per SM
@@ -34,6 +34,7 @@ struct EncWave {
     u64 *elemA, *elemB;
     u64 *triples[ST_COUNT];     // [ST_SEQ] really holds u32 (tr_make32)
     u32 *hist;
+    u32 *scanpart;              // chunk sums of the histogram scan, [B][ceil(D * maxtiles / 4096)]
     u64 *seglist; u32 segcap; u32 *nseg;   // nseg[0] count, nseg[1..2] work cursors
     u8 *obuf;                   // range-coder scratch
     u8 *sidebuf;

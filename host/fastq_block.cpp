@@ -1,6 +1,11 @@
 #include "fastq_block.h"
 
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 
@@ -11,31 +16,42 @@ namespace sqhost {
 
 bool InFile::open(const std::string &path) {
     close();
-    FILE *f = fopen(path.c_str(), "rb");
-    if (!f) return false;
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
     unsigned char magic[2] = {0, 0};
-    size_t k = fread(magic, 1, 2, f);
+    ssize_t k = ::pread(fd, magic, 2, 0);
     if (k == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {       // gzip member
-        fclose(f);
+        ::close(fd);
         gzFile g = gzopen(path.c_str(), "rb");
         if (g) gzbuffer(g, 1 << 20);
         f_ = g;
         return f_ != nullptr;
     }
-    rewind(f);
-    setvbuf(f, nullptr, _IOFBF, 1 << 20);
-    plain_ = f;
+    fd_ = fd;                                                    // plain: read(2) straight into the caller's buffer
     return true;
 }
 void InFile::close() {
     if (f_) gzclose((gzFile)f_);
-    if (plain_) fclose(plain_);
+    if (fd_ >= 0) ::close(fd_);
     f_ = nullptr;
-    plain_ = nullptr;
+    fd_ = -1;
+    gbuf_.clear(); gpos_ = 0;
 }
 size_t InFile::read(void *dst, size_t n) {
-    if (plain_) return fread(dst, 1, n, plain_);
     size_t got = 0;
+    if (fd_ >= 0) {
+        if (gpos_ < gbuf_.size()) {                              // bytes getline() read ahead
+            got = std::min(n, gbuf_.size() - gpos_);
+            memcpy(dst, gbuf_.data() + gpos_, got);
+            gpos_ += got;
+        }
+        while (got < n) {
+            ssize_t k = ::read(fd_, (char *)dst + got, n - got);
+            if (k <= 0) break;
+            got += (size_t)k;
+        }
+        return got;
+    }
     while (got < n) {
         unsigned chunk = (unsigned)std::min<size_t>(n - got, 1u << 30);
         int r = gzread((gzFile)f_, (char *)dst + got, chunk);
@@ -45,9 +61,28 @@ size_t InFile::read(void *dst, size_t n) {
     return got;
 }
 bool InFile::getline(std::vector<char> &out) {
+    if (fd_ >= 0) {
+        bool any = false;
+        for (;;) {
+            if (gpos_ >= gbuf_.size()) {
+                gbuf_.resize(1 << 20);
+                ssize_t k = ::read(fd_, gbuf_.data(), gbuf_.size());
+                gbuf_.resize(k > 0 ? (size_t)k : 0);
+                gpos_ = 0;
+                if (gbuf_.empty()) return any;
+            }
+            const char *p = gbuf_.data() + gpos_, *e = gbuf_.data() + gbuf_.size();
+            const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+            const char *stop = q ? q + 1 : e;
+            out.insert(out.end(), p, stop);
+            gpos_ += (size_t)(stop - p);
+            any = true;
+            if (q) return true;
+        }
+    }
     char buf[1 << 16];
     bool any = false;
-    while (plain_ ? fgets(buf, sizeof buf, plain_) != nullptr : gzgets((gzFile)f_, buf, sizeof buf) != nullptr) {
+    while (gzgets((gzFile)f_, buf, sizeof buf) != nullptr) {
         size_t n = strlen(buf);
         out.insert(out.end(), buf, buf + n);
         any = true;
@@ -95,14 +130,24 @@ bool BlockReader::next_text(std::vector<char> &t1, std::vector<char> &t2) {
     for (int k = 0; k < nf; k++) {
         std::vector<char> &b = *t[k];
         size_t L = left_[k].size();
-        b.resize(quota + 1);
-        memcpy(b.data(), left_[k].data(), L);
-        left_[k].clear();
         size_t want = quota > L ? quota - L : 0;
-        size_t got = want ? f_[k].read(b.data() + L, want) : 0;
+        // leftover first, then the file: the bytes are appended in chunks so that no byte is written twice
+        // (a resize to the quota would zero-fill 25 MiB per mate and block on the single reader thread)
+        b.reserve(L + want + 1);
+        b.assign(left_[k].begin(), left_[k].end());
+        left_[k].clear();
+        size_t got = 0;
+        while (got < want) {
+            const size_t chunk = std::min<size_t>(want - got, 4u << 20);
+            const size_t at = b.size();
+            b.resize(at + chunk);                     // 4 MiB at a time stays in cache between the fill and the read
+            size_t k2 = f_[k].read(b.data() + at, chunk);
+            b.resize(at + k2);
+            got += k2;
+            if (k2 < chunk) break;
+        }
         if (first_[k].empty()) first_line(b.data() + L, got, first_[k]);
         if (got < want) shortread[k] = true;
-        b.resize(L + got);
     }
     // doReadJob @0x432a80 ends on a short read; doReadPEJob ends only when BOTH files came up short in the same
     // round (@0x432ec2-0x432ede: got[0] >= want[0] || got[1] >= want[1] keeps cutting).  Mates of unequal byte
@@ -124,15 +169,23 @@ bool BlockReader::next_text(std::vector<char> &t1, std::vector<char> &t2) {
     // cultPEbuf @0x432180 (cut = true): newline positions of both buffers, back off two lines from the
     // shorter one, find the record start in file 1, cut file 2 after the same number of lines
     std::vector<int> nl[2];
-    for (int k = 0; k < 2; k++) {                                    // memchr: this scan is on the single reader thread
-        const char *b0 = t[k]->data(), *end = b0 + t[k]->size();
-        nl[k].reserve(t[k]->size() / 64);
-        for (const char *p = b0; p < end;) {
-            const char *q = (const char *)memchr(p, '\n', (size_t)(end - p));
-            if (!q) break;
-            nl[k].push_back((int)(q - b0));
-            p = q + 1;
+    for (int k = 0; k < 2; k++) {                                    // this scan is on the single reader thread: 16 bytes per compare
+        const char *b0 = t[k]->data();
+        const size_t n = t[k]->size();
+        nl[k].resize(n / 32 + 64);
+        size_t cnt = 0, i = 0;
+#if defined(__SSE2__)
+        const __m128i nlv = _mm_set1_epi8('\n');
+        for (; i + 16 <= n; i += 16) {
+            unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i *)(b0 + i)), nlv));
+            if (!m) continue;
+            if (cnt + 16 > nl[k].size()) nl[k].resize(nl[k].size() * 2);
+            while (m) { nl[k][cnt++] = (int)(i + (unsigned)__builtin_ctz(m)); m &= m - 1; }
         }
+#endif
+        for (; i < n; i++)
+            if (b0[i] == '\n') { if (cnt + 1 > nl[k].size()) nl[k].resize(nl[k].size() * 2); nl[k][cnt++] = (int)i; }
+        nl[k].resize(cnt);
     }
     int nmin = (int)std::min(nl[0].size(), nl[1].size());
     if (nmin < 3) throw std::runtime_error("block too small to cut a paired-end buffer");

@@ -39,14 +39,16 @@ public:
     ~InFile() { close(); }
     bool open(const std::string &path);
     void close();
-    bool ok() const { return f_ != nullptr || plain_ != nullptr; }
+    bool ok() const { return f_ != nullptr || fd_ >= 0; }
     size_t read(void *dst, size_t n);                 // like fread(dst, 1, n)
     bool getline(std::vector<char> &append_to);       // appends one line including its '\n'; false at end of input
     static bool is_gz_name(const std::string &path) { return path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0; }
 
 private:
     void *f_ = nullptr;                               // gzFile (gzip input)
-    FILE *plain_ = nullptr;                           // plain input: read directly, no pass through zlib's buffer
+    int fd_ = -1;                                     // plain input: read(2) straight from the page cache, no stdio copy
+    std::vector<char> gbuf_;                          // read-ahead of getline()
+    size_t gpos_ = 0;
 };
 
 class BlockReader {
