@@ -64,6 +64,31 @@ def test_ragged_reads_with_degenerate_bases(fq):
     check(fq, [ragged_block(1, 3000), ragged_block(2, 1500, id_style=1), ragged_block(3, 1, maxlen=50)])
 
 
+def low_complexity_block(seed, nreads=1500):
+    """Homopolymers and short tandem repeats (periods 1..6), runs of one quality value: the base decoder's context word is
+    then re-used inside its look-ahead window (the forwarding log), the quality decoder stays in one context for many
+    symbols (the same-context path), and contexts saturate (the halving paths of both models)."""
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(nreads):
+        L = int(rng.integers(20, 400))
+        period = int(rng.integers(1, 7))
+        unit = rng.choice(np.frombuffer(b"ACGT", np.uint8), period)
+        seq = np.tile(unit, L // period + 1)[:L].copy()
+        for _ in range(int(rng.integers(0, 4))):                # a few point changes break the period
+            seq[int(rng.integers(0, L))] = rng.choice(np.frombuffer(b"ACGTN", np.uint8))
+        qual = np.full(L, 33 + int(rng.integers(2, 41)), np.uint8)
+        k = int(rng.integers(0, L))
+        qual[k:] = 33 + int(rng.integers(2, 41))                # two runs per read
+        recs.append((b"lc%d/%d" % (i, period), seq.tobytes(), qual.tobytes()))
+    return po.block_from_records(recs)
+
+
+def test_low_complexity_reads(fq):
+    check(fq, [low_complexity_block(21), low_complexity_block(22, 4000)])
+    check(fq, [low_complexity_block(23)], slevel=0)             # order-7 contexts repeat even sooner
+
+
 def test_encode_parity_on_inputs_the_reference_cannot_round_trip(fq):
     check(fq, [ragged_block(9, 2000, empty=True)], roundtrip=False)
 
