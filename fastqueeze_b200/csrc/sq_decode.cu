@@ -152,8 +152,8 @@ template <int EPL> struct WReg { u32 w[EPL]; u32 bt; };
 // L2 residency hints.  The warp-model tables (hot set: a few hundred KB per block) must survive in L2
 // beside the base-context tables, whose accesses are uniformly random over 4 MB per block and would
 // otherwise evict them: models are accessed evict_last, base-context sectors evict_first.
-SQ_D u64 l2_policy_keep() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-SQ_D u64 l2_policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+SQ_D u64 l2_policy_keep() { u64 p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+SQ_D u64 l2_policy_stream() { u64 p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 #ifndef SQ_L2_HINTS
 #define SQ_L2_HINTS 2          // 0: none, 1: everywhere, 2: base-context accesses only (measured best)
 #endif
@@ -319,6 +319,10 @@ __global__ void __launch_bounds__(256) k_init_q4(DecBlock *db, u32 nmodels, cons
         }
         u32 base = warp_incl_scan_d(T, lane) - T;
         u32 c1 = (base + f[0]) & 0xffffu, c2 = (base + f[0] + f[1]) & 0xffffu, c3 = (base + T) & 0xffffu;
+        if (SQ_QF < 32) {                                  // tail lanes hold their sums relative to the front's total
+            const u32 F = __shfl_sync(FULL, c3, SQ_QF - 1);
+            if (lane >= SQ_QF) { c1 = (c1 - F) & 0xffffu; c2 = (c2 - F) & 0xffffu; c3 = (c3 - F) & 0xffffu; }
+        }
         uint4 v;
         v.x = c1 | (c2 << 16);
         v.y = c3 | (tot << 16);
@@ -429,17 +433,59 @@ struct RcWin {
     }
 };
 
+// L2 hints in the two long chains (measured on the full job, 274 blocks resident): the base-context ring copies and
+// stores marked evict_first: decode 7.37 -> 7.04 s (they stream 1.5 TB through the L2 the quality models live in);
+// the quality models marked evict_last on top of that: no change.  The hint rides in the instruction's descriptor:
+// no instruction is added.
+#ifndef SQ_POL_QUAL
+#define SQ_POL_QUAL 0
+#endif
+#ifndef SQ_POL_BASE
+#define SQ_POL_BASE 1
+#endif
+#if SQ_POL_QUAL
+#define SQ_QPOL_ASM ".L2::cache_hint"
+#define SQ_QPOL_ARG(n) ", %" #n
+#define SQ_QPOL_IN , "l"(l2_policy_keep())
+#else
+#define SQ_QPOL_ASM ""
+#define SQ_QPOL_ARG(n) ""
+#define SQ_QPOL_IN
+#endif
 SQ_D uint4 q4_ld(const uint4 *p) {
     uint4 v;
-    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.global" SQ_QPOL_ASM ".v4.u32 {%0,%1,%2,%3}, [%4]" SQ_QPOL_ARG(5) ";" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) SQ_QPOL_IN : "memory");
     return v;
 }
 SQ_D void q4_st(uint4 *p, const uint4 &v) {
-    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("st.global" SQ_QPOL_ASM ".v4.u32 [%0], {%1,%2,%3,%4}" SQ_QPOL_ARG(5) ";" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) SQ_QPOL_IN : "memory");
 }
 SQ_D u32 shl_clamp(u32 v, u32 n) { u32 r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 
-// rare: TotFreq passed 0xffe0 (@0x4222b7): halve every frequency, rebuild the cumulative sums
+// Front / tail split of a model.  The bubble swaps keep a context's frequent symbols at the head of its table, and the
+// symbols a data set never uses (55 of 95 for Illumina qualities) stay behind them with frequency 1.  Per symbol only the
+// FRONT is touched: the first SQ_QF 16-byte words = 3 SQ_QF entries (2 cache lines instead of 4 for SQ_QF = 16).  Lanes
+// >= SQ_QF load the SAME word as lane - SQ_QF (no extra lines): every lane then has tot / the reciprocal / the bubble
+// count and all conditions stay warp-uniform; their hit predicate is forced off and they never store.  The remaining
+// words (the TAIL) hold their cumulative sums RELATIVE to the front's total F: a front update adds 8 to F and to every
+// absolute sum behind it, so the relative form does not change.  A symbol in the tail (all front lanes miss) and the
+// halving of a model take the whole model, one word per lane, straight from memory (q4_full_*): registers and memory
+// agree at those points.  The tail test is NOT a branch on the symbol chain: the step runs on speculatively (a branch
+// after the ballot cost 40 of 360 cycles) with a coder update that is the identity, and the step's closing branch redoes
+// it on the whole model.  Measured on the full job: the quality chain 12.5 -> 11.4 G cycles (fewer L1 / L2 misses with
+// two blocks per SM); a layout with every front word replicated on two neighbouring lanes (no predicates at all) was
+// 30 % slower.
+static_assert(SQ_QF == 32 || SQ_QF == 16 || SQ_QF == 8, "front words per model");
+SQ_D int q4_flane(int lane) { return lane & (SQ_QF - 1); }
+// store of the front words: only the lanes below SQ_QF own one
+SQ_D void q4_stf(uint4 *p, const uint4 &v, int lane) {
+    if (SQ_QF >= 32) { q4_st(p, v); return; }
+    const u32 front = lane < SQ_QF ? 1u : 0u;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global" SQ_QPOL_ASM ".v4.u32 [%0], {%1,%2,%3,%4}" SQ_QPOL_ARG(6) ";\n\t}"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(front) SQ_QPOL_IN : "memory");
+}
+
+// rare: TotFreq passed 0xffe0 (@0x4222b7): halve every frequency, rebuild the cumulative sums (natural layout)
 SQ_D void q4_halve(uint4 &M, int lane) {
     u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
     u32 c0 = __shfl_up_sync(FULL, c3, 1);
@@ -453,8 +499,8 @@ SQ_D void q4_halve(uint4 &M, int lane) {
     M.x = ((base + f0) & 0xffffu) | ((base + f0 + f1) << 16);
     M.y = (inc & 0xffffu) | (tot << 16);
 }
-// every 16th symbol of a model (@0x4222d3-0x4222f1): swap the coded entry with its predecessor when its
-// frequency is strictly greater.  kl / li locate the coded entry (li is only meaningful on lane kl).
+// every 16th symbol of a model (@0x4222d3-0x4222f1): swap the coded entry with its predecessor when its frequency is
+// strictly greater.  kl / li locate the coded entry (li is only meaningful on lane kl).
 SQ_D void q4_bubble(uint4 &M, int kl, int li, int lane) {
     u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
     u32 c0 = __shfl_up_sync(FULL, c3, 1);
@@ -481,81 +527,62 @@ SQ_D void q4_bubble(uint4 &M, int kl, int li, int lane) {
     }
 }
 
-// One quality symbol (decode_qual @0x42a750; decodeSymbol inlined @0x42a7d0-0x42a960).  M is the model of
-// context `last` (this lane's 16 bytes).  The next model's load is issued as soon as the symbol is known;
-// the coder step, the output byte and this model's update + write-back fill its latency.
+// the whole model `ctx` in its natural layout (lane l = word l), tail sums made absolute; tabf = table + q4_flane(lane)
+SQ_D uint4 q4_full_in(const uint4 *tabf, u32 ctx, int lane) {
+    __syncwarp();
+    uint4 N = q4_ld(tabf + (u64)ctx * 32 + (lane - q4_flane(lane)));
+    if (SQ_QF < 32) {
+        const u32 F = __shfl_sync(FULL, N.y & 0xffffu, SQ_QF - 1);
+        const u32 y0 = __shfl_sync(FULL, N.y, 0), z0 = __shfl_sync(FULL, N.z, 0), w0 = __shfl_sync(FULL, N.w, 0);
+        if (lane >= SQ_QF) {
+            N.x += F * 0x10001u;
+            N.y = (y0 & 0xffff0000u) | ((N.y + F) & 0xffffu);
+            N.z = z0;
+            N.w = (w0 & 0xff000000u) | (N.w & 0x00ffffffu);
+        }
+    }
+    return N;
+}
+SQ_D void q4_full_out(uint4 *tabf, u32 ctx, const uint4 &N, int lane) {
+    uint4 V = N;
+    if (SQ_QF < 32) {
+        const u32 F = __shfl_sync(FULL, N.y & 0xffffu, SQ_QF - 1);
+        if (lane >= SQ_QF) { V.x = N.x - F * 0x10001u; V.y = (N.y & 0xffff0000u) | ((N.y - F) & 0xffffu); }
+    }
+    q4_st(tabf + (u64)ctx * 32 + (lane - q4_flane(lane)), V);
+    __syncwarp();
+}
+
+// context of the next symbol (encode_qual @0x422474-0x422505); 0 opens the next read.
 // SAT: delta has reached 56 in this read (it only grows), so its context bits are constant.
 template <int QLEVEL, bool SAT>
-SQ_D u32 q4_step(uint4 &M, u32 &last, RcWin &rc, uint4 *tab, u8 *qout, int i, int len, u32 &q1, u32 &q2, u32 &delta, int lane) {
-    const u32 tot = M.y >> 16;
-    const u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
-    u32 c0 = __shfl_up_sync(FULL, c3, 1);
-    c0 = lane ? c0 : 0u;
-    // r = range / tot
-    u32 r = __umulhi(rc.range, M.z);
-    u32 rem = rc.range - r * tot;
-    r += (rem >= tot) ? 1u : 0u;
-    const u32 code = rc.code;
-    const u32 miss = __ballot_sync(FULL, code >= c3 * r);
-    const int kl = __popc(miss);                          // hits are monotone in the lane index
-    const bool p1 = code >= c1 * r, p2 = code >= c2 * r;   // monotone: p2 implies p1
-    const int li = (int)p1 + (int)p2;
-    const u32 cex = p2 ? c2 : (p1 ? c1 : c0);
-    const u32 cnx = p2 ? c3 : (p1 ? c2 : c1);
-    u32 A = cex | ((cnx - cex) << 16);
-    const u32 sy = __byte_perm(M.w, 0, 0x4440u | (u32)li);
-    const u32 qq = __shfl_sync(FULL, sy, kl);
-    A = __shfl_sync(FULL, A, kl);
-    // context of the next symbol (encode_qual @0x422474-0x422505); 0 opens the next read
-    const bool more = i + 1 < len;
-    const u32 amax = (q1 > q2 ? q1 : q2) << 6;
+SQ_D u32 q4_next_ctx(u32 qq, u32 q1, u32 q2, u32 &delta, bool more, int i) {
+    const u32 amax = q1 > q2 ? q1 : q2;
     u32 K = 0;
     if (QLEVEL > 1) K |= (u32)(q1 == q2) << 12;
     if (QLEVEL > 2) K |= (i <= 111) ? (u32)((i + 15) & 0x78) << 13 : 0xf0000u;
-    u32 nl;
     if (SAT || QLEVEL == 1) {
         if (QLEVEL > 1) K |= (56u & 0xf8u) << 10;
         const u32 mk = more ? 0xfffu : 0u;
         K = more ? K : 0u;
-        nl = ((amax + qq) & mk) | K;
-    } else {
-        int dd = (int)q1 - (int)qq;
-        u32 d2 = delta + (u32)(dd > 0 ? dd : 0);
-        nl = (((amax + qq) & 0xfffu) | K | (((d2 < 56 ? d2 : 56u) & 0xf8u) << 10)) & (more ? 0xffffffffu : 0u);
-        delta = d2;
+        return ((amax * 64 + qq) & mk) | K;
     }
-    const uint4 Mn = q4_ld(tab + (u64)nl * 32);
-    // ---- off the symbol chain from here
-    rc.range = r;
-    rc.decode(A & 0xffffu, A >> 16);
-    if (lane == 0) qout[i] = (u8)(qq + 33);
-    // Freq += 8, TotFreq += 8 (@0x4222a0): every cumulative sum at or above the coded entry moves
-    const bool ge = lane >= kl;
-    const u32 lik = lane == kl ? (u32)li : 0u;
-    M.x += ge ? shl_clamp(0x00080008u, 16u * lik) : 0u;
-    M.y += (ge ? 8u : 0u) + (8u << 16);
-    u32 bub = ((M.w >> 24) + 1) & 15u;
-    M.w = (M.w & 0x00ffffffu) | (bub << 24);
-    if (tot + 8 > 0xffe0u) q4_halve(M, lane);
-    if (bub == 0) q4_bubble(M, kl, li, lane);
-    M.z = recip32(M.y >> 16);
-    q4_st(tab + (u64)last * 32, M);
-    const bool same = nl == last;
-    M.x = same ? M.x : Mn.x; M.y = same ? M.y : Mn.y; M.z = same ? M.z : Mn.z; M.w = same ? M.w : Mn.w;
-    last = nl;
-    q2 = q1; q1 = qq;
-    return qq;
+    int dd = (int)q1 - (int)qq;
+    u32 d2 = delta + (u32)(dd > 0 ? dd : 0);
+    delta = d2;
+    return (((amax * 64 + qq) & 0xfffu) | K | (((d2 < 56 ? d2 : 56u) & 0xf8u) << 10)) & (more ? 0xffffffffu : 0u);
 }
 
-// Software-pipelined form of the same step.  A warp issues in order and at best one instruction every other
-// cycle, so what a symbol costs is (a) its instruction COUNT and (b) how well independent chains interleave.
-// The common-case update of model i (none of it on the symbol chain) is therefore DEFERRED: it is carried as a
-// pending record into the next step and sits in the same basic block as that step's search.  Cases the deferred
-// form cannot take are completed on the spot (uniform branch at the end of the step): the next symbol uses the
-// same context, the update halves or runs the 16-symbol bubble check, or the total is too small for the one-step
-// Newton refresh of the reciprocal.
-//   * the +8 masks come straight from the search predicates: lanes above the symbol's lane compare "code < c1 r"
-//     (add to all three sums), lanes below compare "code >= c3 r" (add nothing), the symbol's lane picks by p1 / p2;
+// Software-pipelined quality step (decode_qual @0x42a750; decodeSymbol inlined @0x42a7d0-0x42a960).  A warp issues in
+// order and at best one instruction every other cycle, so what a symbol costs is (a) its instruction COUNT and (b) how
+// well independent chains interleave.  The next model's load is issued as soon as the symbol is known.  The common-case
+// update of model i (none of it on the symbol chain) is DEFERRED: it is carried as a pending record into the next step
+// and sits in the same basic block as that step's search.  Cases the deferred form cannot take are completed on the spot
+// (ONE uniform branch at the end of the step): the next symbol uses the same context, the update halves or runs the
+// 16-symbol bubble check, the total is too small for the one-step Newton refresh of the reciprocal, or the symbol was
+// not among the front entries (then the step so far was a no-op on the coder and is redone on the whole model).
+//   * the +8 masks come straight from the search predicates: lanes above the symbol's compare "code < c1 r" (add to all
+//     three sums), lanes below compare "code >= c3 r" (add nothing), the symbol's own pick by p1 / p2;
 //   * reciprocal of tot + 8 from the reciprocal of tot: e1 = e - mulhi(e, e (tot + 8) - 2^32) is ceil(E (1 - d^2)),
 //     d <= 8 / tot, i.e. floor(E) or ceil(E) once 2^38 / tot^3 < 1: one downward fix-up (SQ_Q_NEWTON_MIN).
 struct QPend { uint4 M; u32 ctx, addx, addy; };
@@ -563,7 +590,7 @@ struct QPend { uint4 M; u32 ctx, addx, addy; };
 
 SQ_D void q4_pend_none(QPend &P, u32 dummy_ctx) { P.M = make_uint4(0, 0x20000000u, 0x20000u, 0); P.ctx = dummy_ctx; P.addx = 0; P.addy = 0; }
 
-SQ_D void q4_apply(uint4 *tab, const QPend &P) {
+SQ_D void q4_apply(uint4 *tab, const QPend &P, int lane) {
     uint4 Q = P.M;
     Q.x += P.addx;
     Q.y += P.addy;
@@ -573,9 +600,60 @@ SQ_D void q4_apply(uint4 *tab, const QPend &P) {
     e -= __umulhi(e, e * d);                          // e * d - 2^32 fits 32 bits: the old reciprocal overshoots the new total
     if ((i32)(e * d) >= 0) e--;                       // e * d wrapped past 2^32 - 1
     Q.z = e;
-    q4_st(tab + (u64)P.ctx * 32, Q);
+    q4_stf(tab + (u64)P.ctx * 32, Q, lane);
 }
 
+// One symbol on the WHOLE model of context `last` (memory holds its current state): the symbol lies behind the front
+// entries.  Search over the natural layout, update, halving (@0x4222b7), bubble check (@0x4222d3), reciprocal by
+// division, front and tail written back; returns with the next model's front loaded.  r = range / tot.
+template <int QLEVEL, bool SAT>
+SQ_D u32 q4_full_step(uint4 &M, u32 &last, QPend &P, RcWin &rc, uint4 *tab, u8 *qp, bool more, int i, u32 &q1, u32 &q2, u32 &delta,
+                      int lane, u32 dummy_ctx, u32 r) {
+    uint4 N = q4_full_in(tab, last, lane);
+    const u32 tot = N.y >> 16;
+    const u32 c1 = N.x & 0xffffu, c2 = N.x >> 16, c3 = N.y & 0xffffu;
+    u32 c0 = __shfl_up_sync(FULL, c3, 1);
+    c0 = lane ? c0 : 0u;
+    const u32 code = rc.code;
+    const bool p1 = code >= c1 * r, p2 = code >= c2 * r, p3 = code >= c3 * r;
+    const int kl = __popc(__ballot_sync(FULL, p3));
+    const int li = (p1 ? 1 : 0) + (p2 ? 1 : 0);
+    const u32 cex = p2 ? c2 : (p1 ? c1 : c0);
+    const u32 cnx = p2 ? c3 : (p1 ? c2 : c1);
+    u32 A = ((cnx - cex) << 16) + cex;
+    const u32 sy = __byte_perm(N.w, 0, 0x4440u + (u32)li);
+    const u32 qq = __shfl_sync(FULL, sy, kl);
+    A = __shfl_sync(FULL, A, kl);
+    const u32 nl = q4_next_ctx<QLEVEL, SAT>(qq, q1, q2, delta, more, i);
+    rc.range = r;
+    rc.decode(A & 0xffffu, A >> 16);
+    if (lane == 0) *qp = (u8)(qq + 33);
+    N.x += p2 ? 0u : (p1 ? 0x00080000u : 0x00080008u);
+    N.y += p3 ? 0x00080000u : 0x00080008u;
+    const bool bubdue = ((N.w + (1u << 24)) & (15u << 24)) == 0;
+    N.w = (N.w & 0xf0ffffffu) | ((N.w + (1u << 24)) & (15u << 24));
+    if (tot + 8 > 0xffe0u) q4_halve(N, lane);
+    if (bubdue) q4_bubble(N, kl, li, lane);
+    N.z = recip32(N.y >> 16);
+    q4_full_out(tab, last, N, lane);
+    M = q4_ld(tab + (u64)nl * 32);
+    q4_pend_none(P, dummy_ctx);
+    last = nl;
+    q2 = q1; q1 = qq;
+    return qq;
+}
+
+// the model of `ctx` (memory holds its state after this symbol's update) passed 0xffe0: halve all of it, then the
+// bubble check of the coded entry (kn = its word, li = its index in the word), new reciprocal, written back
+SQ_D void q4_full_halve(uint4 *tab, u32 ctx, bool bubdue, int kn, int li, int lane) {
+    uint4 N = q4_full_in(tab, ctx, lane);
+    q4_halve(N, lane);
+    if (bubdue) q4_bubble(N, kn, li, lane);
+    N.z = recip32(N.y >> 16);
+    q4_full_out(tab, ctx, N, lane);
+}
+
+// tab = table + q4_flane(lane)
 template <int QLEVEL, bool SAT>
 SQ_D u32 q4_pstep(uint4 &M, u32 &last, QPend &P, RcWin &rc, uint4 *tab, u8 *qp, bool more, int i, u32 &q1, u32 &q2, u32 &delta,
                   int lane, u32 dummy_ctx) {
@@ -583,60 +661,59 @@ SQ_D u32 q4_pstep(uint4 &M, u32 &last, QPend &P, RcWin &rc, uint4 *tab, u8 *qp, 
     const u32 c1 = M.x & 0xffffu, c2 = M.x >> 16, c3 = M.y & 0xffffu;
     u32 c0 = __shfl_up_sync(FULL, c3, 1);
     c0 = lane ? c0 : 0u;
-    q4_apply(tab, P);                                 // previous symbol's model (or the dummy slot): interleaves with the search below
+    q4_apply(tab, P, lane);                           // previous symbol's model (or the dummy slot): interleaves with the search below
     u32 r = __umulhi(rc.range, M.z);
     r += (rc.range - r * tot >= tot) ? 1u : 0u;
     const u32 code = rc.code;
-    const bool p1 = code >= c1 * r, p2 = code >= c2 * r, p3 = code >= c3 * r;   // monotone
+    const bool p1 = code >= c1 * r, p2 = code >= c2 * r;                        // monotone
+    const bool p3 = SQ_QF >= 32 ? code >= c3 * r : (lane < SQ_QF && code >= c3 * r);
     const u32 miss = __ballot_sync(FULL, p3);
     const int kl = __popc(miss);                      // hits are monotone in the lane index
+    const bool tail = SQ_QF < 32 && kl >= SQ_QF;      // not among the front entries
     const u32 cex = p2 ? c2 : (p1 ? c1 : c0);
     const u32 cnx = p2 ? c3 : (p1 ? c2 : c1);
     u32 A = ((cnx - cex) << 16) + cex;
     const u32 sy = __byte_perm(M.w, 0, 0x4440u + (p1 ? 1u : 0u) + (p2 ? 1u : 0u));
     const u32 qq = __shfl_sync(FULL, sy, kl);
     A = __shfl_sync(FULL, A, kl);
-    const u32 addx = p2 ? (p3 ? 0u : 0u) : (p1 ? 0x00080000u : 0x00080008u);
+    const u32 addx = p2 ? 0u : (p1 ? 0x00080000u : 0x00080008u);
     const u32 addy = p3 ? 0x00080000u : 0x00080008u;
-    const u32 amax = q1 > q2 ? q1 : q2;
-    u32 K = 0;
-    if (QLEVEL > 1) K |= (u32)(q1 == q2) << 12;
-    if (QLEVEL > 2) K |= (i <= 111) ? (u32)((i + 15) & 0x78) << 13 : 0xf0000u;
-    u32 nl;
-    if (SAT || QLEVEL == 1) {
-        if (QLEVEL > 1) K |= (56u & 0xf8u) << 10;
-        const u32 mk = more ? 0xfffu : 0u;
-        K = more ? K : 0u;
-        nl = ((amax * 64 + qq) & mk) | K;
-    } else {
-        int dd = (int)q1 - (int)qq;
-        u32 d2 = delta + (u32)(dd > 0 ? dd : 0);
-        nl = (((amax * 64 + qq) & 0xfffu) | K | (((d2 < 56 ? d2 : 56u) & 0xf8u) << 10)) & (more ? 0xffffffffu : 0u);
-        delta = d2;
-    }
+    const u32 delta0 = delta;
+    const u32 nl = q4_next_ctx<QLEVEL, SAT>(qq, q1, q2, delta, more, i);
     const uint4 Mn = q4_ld(tab + (u64)nl * 32);
-    rc.range = r;
-    rc.decode(A & 0xffffu, A >> 16);
+    // tail: (cum 0, freq 1) on the unchanged range leaves the coder as it is; the step is redone below
+    const u32 range0 = rc.range;
+    rc.range = tail ? range0 : r;
+    rc.decode(tail ? 0u : (A & 0xffffu), tail ? 1u : (A >> 16));
     if (lane == 0) *qp = (u8)(qq + 33);
     // deferred unless: same context next, halving (tot + 8 > 0xffe0), total below the Newton range, bubble check due
     const bool special = (M.y - (SQ_Q_NEWTON_MIN << 16)) > (((0xffe0u - 8u - SQ_Q_NEWTON_MIN) << 16) | 0xffffu);
     const bool bubdue = ((M.w + (1u << 24)) & (15u << 24)) == 0;
-    if (nl == last || special || bubdue) {
+    if (nl == last || special || bubdue || tail) {
+        if (tail) {
+            delta = delta0;
+            return q4_full_step<QLEVEL, SAT>(M, last, P, rc, tab, qp, more, i, q1, q2, delta, lane, dummy_ctx, r);
+        }
         M.x += addx;
         M.y += addy;
         M.w = (M.w & 0xf0ffffffu) | ((M.w + (1u << 24)) & (15u << 24));
-        if (special || bubdue) {
-            if (tot + 8 > 0xffe0u) q4_halve(M, lane);
+        if (tot + 8 > 0xffe0u) {                      // the whole model halves
+            q4_stf(tab + (u64)last * 32, M, lane);
+            q4_full_halve(tab, last, bubdue, kl, (p1 ? 1 : 0) + (p2 ? 1 : 0), lane);
+            M = q4_ld(tab + (u64)last * 32);
+        } else {
             if (bubdue) q4_bubble(M, kl, (p1 ? 1 : 0) + (p2 ? 1 : 0), lane);
-            M.z = recip32(M.y >> 16);
-        } else {                                      // the same context again (runs of one quality value): Newton refresh as in q4_apply
-            const u32 d = M.y >> 16;
-            u32 e = M.z;
-            e -= __umulhi(e, e * d);
-            if ((i32)(e * d) >= 0) e--;
-            M.z = e;
+            if (special) {
+                M.z = recip32(M.y >> 16);
+            } else {                                  // Newton refresh as in q4_apply
+                const u32 d = M.y >> 16;
+                u32 e = M.z;
+                e -= __umulhi(e, e * d);
+                if ((i32)(e * d) >= 0) e--;
+                M.z = e;
+            }
+            q4_stf(tab + (u64)last * 32, M, lane);
         }
-        q4_st(tab + (u64)last * 32, M);
         if (nl != last) M = Mn;
         q4_pend_none(P, dummy_ctx);
     } else {
@@ -831,7 +908,7 @@ SQ_D u32 decode_base(u8 *seqtab, u32 *ring, const u32 *rlut, RcWin &rc, u32 &las
 }
 
 // The same step for the bulk of a read (its first SQ_LOOK bases go through decode_base, which reads the table
-// directly): no look-ahead test, no cache-policy operands (they cost more instructions than they save), bytes picked
+// directly): no look-ahead test, bytes picked
 // with PRMT.  A warp issues at best one instruction every other cycle, so the count is what matters here.
 SQ_D u32 lds32(u32 saddr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
 // ring_s / rlut_s: shared-window addresses of the ring and the reciprocal table (computed once per warp);
@@ -839,7 +916,11 @@ SQ_D u32 lds32(u32 saddr) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"
 SQ_D u32 base_step_fast(u8 *seqtab, const u8 *cp_src, u32 cp_dst, u32 ring_s, u32 rlut_s, RcWin &rc, u32 &last, u32 mask, SeqPipe &P, int lane) {
     if (lane < SQ_LOOK_N / 4) {
         const u32 basec = (last << (2 * SQ_LOOK)) & mask;
+#if SQ_POL_BASE
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(cp_dst + (((P.step + SQ_LOOK) & 7) * SQ_LOOK_N * 4)), "l"(cp_src + ((u64)basec << 2)), "l"(l2_policy_stream()) : "memory");
+#else
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(cp_dst + (((P.step + SQ_LOOK) & 7) * SQ_LOOK_N * 4)), "l"(cp_src + ((u64)basec << 2)) : "memory");
+#endif
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group %0;\n" ::"n"(SQ_LOOK) : "memory");
@@ -861,7 +942,11 @@ SQ_D u32 base_step_fast(u8 *seqtab, const u8 *cp_src, u32 cp_dst, u32 ring_s, u3
     rc.decode(cum, cnx - cum);
     u32 nv = x + (0x01010101u << (8 * b));
     if ((nv >> 24) > 253) nv = base_halve(nv);
+#if SQ_POL_BASE
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(seqtab + (u64)last * 4), "r"(nv), "l"(l2_policy_stream()) : "memory");
+#else
     asm volatile("st.global.u32 [%0], %1;" ::"l"(seqtab + (u64)last * 4), "r"(nv) : "memory");
+#endif
     P.lc3 = P.lc2; P.lv3 = P.lv2; P.lc2 = P.lc1; P.lv2 = P.lv1; P.lc1 = P.lc0; P.lv1 = P.lv0; P.lc0 = last; P.lv0 = nv;
     P.step++;
     last = (last * 4 + b) & mask;
@@ -1002,16 +1087,17 @@ SQ_D void md5_chase(DecBlock &d, volatile u32 *qprog, volatile u32 *sprog, const
     if (want_q) { rq.finish(d.qual, total, dig); if (!md5_equal(dig, d.md5[2]) && *status == 0) *status = -10; }
 }
 
+#define SQ_DEC_THREADS 96
 template <int QLEVEL>
-__global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 seqmask, int inline_md5, u32 qdummy) {
+__global__ void __launch_bounds__(SQ_DEC_THREADS) k_dec_main(DecBlock *db, int id_rule, u32 seqmask, int inline_md5, u32 qdummy) {
     constexpr int qlevel = QLEVEL;
     __shared__ __align__(16) MainSmem sm;
     DecBlock &d = db[blockIdx.x];
     int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const u64 pol = wid == 2 ? l2_policy_stream() : l2_policy_keep();
     if (threadIdx.x == 0) { sm.qprog = 0; sm.sprog = 0; sm.side_err = 0; }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.rlut[i] = recip32(i);
     __syncthreads();
+    const u64 pol = wid == 2 ? l2_policy_stream() : l2_policy_keep();
     if (d.status != 0) return;
 #ifdef SQ_DEBUG_TIMING
     long long t_begin = clock64();
@@ -1020,6 +1106,10 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
 #define SQ_TICK(name)
 #endif
     const u32 nreads = d.nreads;
+#ifdef SQ_DBG_SKIP                                               // timing experiments only: drop a role (the output is then wrong)
+    if (wid == 2 && (SQ_DBG_SKIP & 1)) { if (lane == 0) sm.sprog = nreads; return; }
+    if (wid == 0 && (SQ_DBG_SKIP & 2)) return;
+#endif
     const u8 *rec = d.rec;
     const u32 *seqoff = d.seqoff;
     const i32 *seqlen = d.seqlen;
@@ -1050,7 +1140,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
     } else if (wid == 1) {                                     // qualities (decompressQual @0x42aa40, decode_qual @0x42a750)
         RcWin rc;
         rc.start(rec + d.off[7], rec + d.off[7] + d.len[7]);
-        uint4 *tab = (uint4 *)d.qualtab + lane;
+        uint4 *tab = (uint4 *)d.qualtab + q4_flane(lane);            // front words: see q4_pstep
         u8 *qual = d.qual;
         const u32 dummy_ctx = qdummy;                          // spare model slot behind the table: target of "no pending update"
         u32 last = 0;
@@ -1072,7 +1162,7 @@ __global__ void __launch_bounds__(96) k_dec_main(DecBlock *db, int id_rule, u32 
                 qq = q4_pstep<QLEVEL, true>(M, last, P, rc, tab, q + i, i + 1 < len, i, q1, q2, delta, lane, dummy_ctx);
             if (qq == 94) {                                    // the rest of the read is '#' (@0x42a9a0); context 0 opens the next read
                 for (int t = i - 1 + lane; t < len; t += 32) q[t] = '#';
-                q4_apply(tab, P);
+                q4_apply(tab, P, lane);
                 q4_pend_none(P, dummy_ctx);
                 if (last != 0) { M = q4_ld(tab); last = 0; }
             }
@@ -1254,9 +1344,9 @@ cudaError_t sqk_decode(const DecWave &w, cudaStream_t st, u64 *launches) {
 #else
     const int inline_md5 = w.md5 ? 1 : 0;
 #endif
-    if (w.qlevel <= 1) k_dec_main<1><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
-    else if (w.qlevel == 2) k_dec_main<2><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
-    else k_dec_main<3><<<B, 96, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
+    if (w.qlevel <= 1) k_dec_main<1><<<B, SQ_DEC_THREADS, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
+    else if (w.qlevel == 2) k_dec_main<2><<<B, SQ_DEC_THREADS, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
+    else k_dec_main<3><<<B, SQ_DEC_THREADS, 0, st>>>(w.db, w.id_rule, w.seqmask, inline_md5, w.nqual);
     *launches += 2;
     if (w.md5 && !inline_md5) { k_dec_md5<<<cdivd(3ull * B, 32), 32, 0, st>>>(w.db, B, w.id_rule); *launches += 1; }
     return cudaGetLastError();

@@ -60,6 +60,9 @@ cudaError_t sqk_pack(const EncWave &w, int compact, cudaStream_t st, u64 *launch
 // decode side (sq_decode.cu)
 // decoder-private "warp model" tables: (EPL + 1) rows of 32 words per model
 #define SQ_WQ_STRIDE (4 * 32)                                  /* SIMPLE_MODEL<95>, 3 entries per lane */
+#ifndef SQ_QF
+#define SQ_QF 16                                               /* decoder: lanes of a quality model read per symbol (front entries), 8 / 16 / 32 */
+#endif
 #define SQ_WNAME_WORDS (768ull * 9 * 32 + 8192ull * 5 * 32)     /* 768 x <256> (8 per lane) + 8192 x <128> (4 per lane) */
 struct DecBlock {
     const u8 *rec; u64 reclen;          // block record (device)

@@ -89,6 +89,31 @@ def test_low_complexity_reads(fq):
     check(fq, [low_complexity_block(23)], slevel=0)             # order-7 contexts repeat even sooner
 
 
+def wide_quality_block(seed, nreads=2500, lo=0, hi=93, runs=False):
+    """Qualities over the coder's whole alphabet ('!'..'~'): the decoder keeps the head of every quality model in the lanes
+    it reads per symbol and the rest behind (front / tail split); symbols 48..93 start in the tail, bubble forward across
+    the boundary when they are frequent, and models halve with entries on both sides."""
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(nreads):
+        L = int(rng.integers(30, 300))
+        seq = rng.choice(np.frombuffer(b"ACGT", np.uint8), L)
+        if runs:                                                # few contexts, tens of thousands of symbols each: halving
+            vals = rng.integers(lo, hi + 1, 3)
+            qual = vals[rng.integers(0, 3, L)]
+            qual = np.where(rng.random(L) < 0.02, rng.integers(0, 94, L), qual)
+        else:
+            qual = rng.integers(lo, hi + 1, L)
+        recs.append((b"wq%d" % i, seq.tobytes(), (qual + 33).astype(np.uint8).tobytes()))
+    return po.block_from_records(recs)
+
+
+def test_wide_quality_alphabet(fq):
+    check(fq, [wide_quality_block(31), wide_quality_block(32, lo=50, hi=93), wide_quality_block(33, 6000, lo=40, hi=60, runs=True)])
+    check(fq, [wide_quality_block(34, 1500), wide_quality_block(35, 4000, lo=44, hi=52, runs=True)], qlevel=1)
+    check(fq, [wide_quality_block(36, 1500, lo=20, hi=80)], qlevel=3)
+
+
 def test_encode_parity_on_inputs_the_reference_cannot_round_trip(fq):
     check(fq, [ragged_block(9, 2000, empty=True)], roundtrip=False)
 
