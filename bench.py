@@ -357,6 +357,10 @@ class Workload:
             r = self.L_.sq_rblock(self.h, q.ctypes.data, q.shape[0], 1.15)
             assert r == 0 and np.array_equal(q, self.dec[0]["qual"].cpu().numpy()), "decoded qualities are not rblock(input)"
 
+    def release(self):
+        """Drop the device-resident copy of the job (inputs, records, decoded output)."""
+        self.blocks, self.recbuf, self.dec = [], [], []
+
     def record_lens(self):
         return [int(self.outs[i].len) for i in range(self.n)]
 
@@ -395,10 +399,14 @@ def train_snapshot(torch, L_, _lib, h, dev, shape, units):
     r = L_.sq_train_model(h, sin, 1, blob.ctypes.data, blob.shape[0])
     if r:
         raise SystemExit("train failed: %d %s" % (r, L_.sq_last_error(h)))
+    load_snapshot(L_, h, blob)
+    return blob, npairs
+
+
+def load_snapshot(L_, h, blob):
     r = L_.sq_load_model(h, blob.ctypes.data, blob.shape[0])
     if r:
         raise SystemExit("load model failed: %d %s" % (r, L_.sq_last_error(h)))
-    return blob.shape[0], npairs
 
 
 def main():
@@ -473,6 +481,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    snapshot = [None]
+
     def measure(block_ids, steps, warmup, label):
         """Build the rank's share, run warmup + timed steps; returns (workload, max-over-ranks ms, clocks)."""
         t0 = time.perf_counter()
@@ -480,9 +490,9 @@ def main():
         w = Workload(torch, L_, _lib, None, stream, dev, shape, cfg, block_ids, units)
         h = w.h = make_ctx(L_, _lib, local, stream, cfg, usemodel)
         if usemodel:
-            nbytes, npairs = train_snapshot(torch, L_, _lib, h, dev, shape, units)
+            snapshot[0], npairs = train_snapshot(torch, L_, _lib, h, dev, shape, units)
             torch.cuda.empty_cache()
-            log("rank %d: trained the %d-byte model snapshot on %d %s (pre-process, untimed)" % (rank, nbytes, npairs, "pairs" if shape.pe else "reads"))
+            log("rank %d: trained the %d-byte model snapshot on %d %s (pre-process, untimed)" % (rank, snapshot[0].shape[0], npairs, "pairs" if shape.pe else "reads"))
         log("rank %d: %s: %d blocks (%.1f MB FASTQ) ready in %.1fs" % (rank, label, w.n, w.fastq_bytes / 1e6, time.perf_counter() - t0))
         for _ in range(warmup):
             w.step_device()
@@ -520,7 +530,14 @@ def main():
     enc_ms, dec_ms = float(tms[0].item()), float(tms[1].item())
     wave_blocks = int(L_.sq_last_wave_blocks(h))
 
-    # ---- e2e through the host-buffer C ABI (pinned host memory, copies inside the timed region)
+    in_bytes_rank, n_rank = w.in_bytes, w.n
+    cpu_sample = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cpu_sample = [to_host(torch, w.blocks[i]) for i in range(min(a.cpu_sample_blocks or max(16, 2 * cores), w.n))]
+
+    # ---- e2e through the host-buffer C ABI (pinned host memory, copies inside the timed region).  What a caller with
+    # host buffers sees: nothing of the job is resident on the device beforehand, so the device-resident copy above is
+    # released and the context is created anew (its workspace is sized from the free HBM).
     e2e = None
     if not a.no_e2e and w.n:
         blocks = w.blocks
@@ -533,6 +550,14 @@ def main():
         eblocks = int(max(1, min(w.n, (0.5 * avail / local_world) // per_block)))
         hb = [to_host(torch, b, pin=True) for b in blocks[:eblocks]]
         hrec = [torch.empty(w.cap, dtype=torch.uint8).pin_memory().numpy() for _ in range(eblocks)]
+        cap = w.cap
+        L_.sq_destroy(h)
+        del blocks
+        w.release()
+        torch.cuda.empty_cache()
+        h = make_ctx(L_, _lib, local, stream, cfg, usemodel)
+        if usemodel:
+            load_snapshot(L_, h, snapshot[0])
         want0 = (hb[0]["seq"].tobytes(), hb[0]["ids"].tobytes())
         hins = (_lib.SqBlockIn * eblocks)()
         houts = (_lib.SqBlockOut * eblocks)()
@@ -544,21 +569,35 @@ def main():
             hins[i].ids, hins[i].seq, hins[i].qual = b["ids"].ctypes.data, b["seq"].ctypes.data, b["qual"].ctypes.data
             hins[i].idlen, hins[i].seqlen = b["idlen"].ctypes.data, b["seqlen"].ctypes.data
             hins[i].idbytes, hins[i].seqbytes = b["ids"].shape[0], b["seq"].shape[0]
-            houts[i].data, houts[i].cap = hrec[i].ctypes.data, w.cap
+            houts[i].data, houts[i].cap = hrec[i].ctypes.data, cap
             hrecs[i] = hrec[i].ctypes.data
             hdecs[i].ids, hdecs[i].idcap = b["ids"].ctypes.data, b["ids"].shape[0]
             hdecs[i].seq, hdecs[i].qual, hdecs[i].seqcap = b["seq"].ctypes.data, b["qual"].ctypes.data, b["seq"].shape[0]
             hdecs[i].idlen, hdecs[i].seqlen, hdecs[i].readcap = b["idlen"].ctypes.data, b["seqlen"].ctypes.data, b["nreads"]
 
+        e2e_ms = {}
+
+        def last_copies(prefix, wall_s):
+            names = (C.c_char_p * 64)()
+            ms = (C.c_float * 64)()
+            for j in range(L_.sq_last_timings(h, names, ms, 64)):
+                if names[j].decode() in ("h2d", "d2h"):
+                    e2e_ms[prefix + names[j].decode()] = round(float(ms[j]), 1)
+            e2e_ms[prefix + "call"] = round(wall_s * 1e3, 1)
+
         def step_host():
+            t = time.perf_counter()
             r = L_.sq_encode_blocks(h, hins, eblocks, houts)
             if r:
                 raise SystemExit("host encode failed: %d %s" % (r, L_.sq_last_error(h)))
+            last_copies("enc.", time.perf_counter() - t)
             for i in range(eblocks):
                 hlens[i] = houts[i].len
+            t = time.perf_counter()
             r = L_.sq_decode_blocks(h, hrecs, hlens, eblocks, hdecs)
             if r:
                 raise SystemExit("host decode failed: %d %s" % (r, L_.sq_last_error(h)))
+            last_copies("dec.", time.perf_counter() - t)
 
         step_host()
         assert (hb[0]["seq"].tobytes(), hb[0]["ids"].tobytes()) == want0
@@ -569,7 +608,7 @@ def main():
             step_host()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
-        sums = torch.tensor([float(eblocks * shape.block_fastq_bytes(units)), float(w.in_bytes * eblocks // w.n),
+        sums = torch.tensor([float(eblocks * shape.block_fastq_bytes(units)), float(in_bytes_rank * eblocks // n_rank),
                              float(sum(int(houts[i].len) for i in range(eblocks))), float(eblocks)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -577,14 +616,13 @@ def main():
         e_fastq, e_in, e_arc, e_blocks = [float(x) for x in sums.tolist()]
         e2e = {"value": round(e_fastq * ksteps / 1e6 / float(dt.item()), 2), "unit": "MB/s",
                "h2d_bytes_per_step": int(e_in + e_arc), "d2h_bytes_per_step": int(e_arc + e_in),
-               "steps": ksteps, "blocks": int(e_blocks)}
+               "steps": ksteps, "blocks": int(e_blocks), "rank0_ms": e2e_ms}
         del hb, hrec
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference binary on a bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu:
-        nb = min(a.cpu_sample_blocks or max(16, 2 * cores), w.n)
-        sample = [to_host(torch, w.blocks[i]) for i in range(nb)]
+    if cpu_sample:
+        sample, nb = cpu_sample, len(cpu_sample)
         rr = reference_run(sample, shape, cfg, cores, 1, 0, a.verbose)
         if rr:
             cpu = {"value": round(rr["value"], 2), "unit": "MB/s", "cores": cores, "kind": "reference",
@@ -592,9 +630,8 @@ def main():
                              % (nb, rr["fastq_bytes"] / 1e6, cores),
                    "compress_MBps": round(rr["compress"], 2), "decompress_MBps": round(rr["decompress"], 2),
                    "entropy_stage_MBps": round(rr.get("entropy_stage_value", 0), 2)}
-        del sample
+        del sample, cpu_sample
 
-    in_bytes_rank, n_rank = w.in_bytes, w.n
     tot = torch.tensor([float(in_bytes_rank), float(n_launch)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot)
@@ -604,6 +641,7 @@ def main():
     replica = None
     if world > 1 and not a.no_replica:
         L_.sq_destroy(h)
+        w.release()
         del w
         torch.cuda.empty_cache()
         w2, h, ms2, _ = measure(range(rank * job_blocks, (rank + 1) * job_blocks), 2, 1, "replica (a whole job per rank)")

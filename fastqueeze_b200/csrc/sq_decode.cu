@@ -689,7 +689,8 @@ SQ_D u32 q4_pstep(uint4 &M, u32 &last, QPend &P, RcWin &rc, uint4 *tab, u8 *qp, 
     // deferred unless: same context next, halving (tot + 8 > 0xffe0), total below the Newton range, bubble check due
     const bool special = (M.y - (SQ_Q_NEWTON_MIN << 16)) > (((0xffe0u - 8u - SQ_Q_NEWTON_MIN) << 16) | 0xffffu);
     const bool bubdue = ((M.w + (1u << 24)) & (15u << 24)) == 0;
-    if (nl == last || special || bubdue || tail) {
+    const bool odd = special || bubdue || tail;
+    if (nl == last || odd) {
         if (tail) {
             delta = delta0;
             return q4_full_step<QLEVEL, SAT>(M, last, P, rc, tab, qp, more, i, q1, q2, delta, lane, dummy_ctx, r);
@@ -697,21 +698,20 @@ SQ_D u32 q4_pstep(uint4 &M, u32 &last, QPend &P, RcWin &rc, uint4 *tab, u8 *qp, 
         M.x += addx;
         M.y += addy;
         M.w = (M.w & 0xf0ffffffu) | ((M.w + (1u << 24)) & (15u << 24));
-        if (tot + 8 > 0xffe0u) {                      // the whole model halves
+        if (!odd) {                                   // the same context again (runs of one quality value): Newton refresh as in q4_apply
+            const u32 d = M.y >> 16;
+            u32 e = M.z;
+            e -= __umulhi(e, e * d);
+            if ((i32)(e * d) >= 0) e--;
+            M.z = e;
+            q4_stf(tab + (u64)last * 32, M, lane);
+        } else if (tot + 8 > 0xffe0u) {               // the whole model halves
             q4_stf(tab + (u64)last * 32, M, lane);
             q4_full_halve(tab, last, bubdue, kl, (p1 ? 1 : 0) + (p2 ? 1 : 0), lane);
             M = q4_ld(tab + (u64)last * 32);
         } else {
             if (bubdue) q4_bubble(M, kl, (p1 ? 1 : 0) + (p2 ? 1 : 0), lane);
-            if (special) {
-                M.z = recip32(M.y >> 16);
-            } else {                                  // Newton refresh as in q4_apply
-                const u32 d = M.y >> 16;
-                u32 e = M.z;
-                e -= __umulhi(e, e * d);
-                if ((i32)(e * d) >= 0) e--;
-                M.z = e;
-            }
+            M.z = recip32(M.y >> 16);
             q4_stf(tab + (u64)last * 32, M, lane);
         }
         if (nl != last) M = Mn;

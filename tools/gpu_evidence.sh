@@ -1,13 +1,13 @@
 #!/bin/bash
 # Round-2 evidence session on one B200: plain runs first, then the same commands under ncu (B200_PROFILING.md recipe)
-O=gpurun_out/r2; mkdir -p $O
+O=gpurun_out/${EV_OUT:-r2}; mkdir -p $O
 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_gpu.log
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 500 > $O/clocks.csv &
 SMI=$!
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; tail -c 600 $O/bench_n1.json; echo
 kill $SMI
 python bench.py --impl reference --steps 1 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err; echo "ref rc=$?"; tail -c 400 $O/bench_reference_arm.json; echo
-for c in se100_q8 pe150_lossy pe150_ref; do
+for c in ${EV_CONFIGS-se100_q8 pe150_lossy pe150_ref}; do
   timeout 900 python bench.py --config $c --steps 1 --warmup 1 > $O/bench_$c.json 2> $O/bench_$c.err; echo "$c rc=$?"
   python - <<PY
 import json

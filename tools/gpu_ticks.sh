@@ -5,7 +5,7 @@ for v in _variants/*.so; do
   cp $v fastqueeze_b200/libseqarc_b200.so
   for nb in ${@:-274}; do
     echo "== $(basename $v) blocks $nb"
-    timeout 400 python bench.py --blocks $nb --steps 1 --warmup 1 --no-cpu --no-e2e 2>&1 | python -c "
+    timeout 400 python bench.py --config ${TICK_CONFIG:-pe150} --blocks $nb --steps 1 --warmup 1 --no-cpu --no-e2e 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('dec warp') and ('qual' in l or 'seq' in l): print('  ', l.strip())
