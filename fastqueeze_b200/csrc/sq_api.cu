@@ -657,7 +657,7 @@ extern "C" int sq_rblock(sq_ctx *c, uint8_t *qual, uint64_t n, double r) {
 namespace {
 
 // EBML-style vint (Encap::getValue @0x4207a0): length from the leading 1 bit
-int get_vint(const u8 *p, const u8 *end, u64 *v) {
+__host__ __device__ int get_vint(const u8 *p, const u8 *end, u64 *v) {
     if (p >= end) return 0;
     int n = 1;
     u8 m = 0x80;
@@ -669,8 +669,9 @@ int get_vint(const u8 *p, const u8 *end, u64 *v) {
     return n;
 }
 
-// walk the tags of one block record on the host (doDecode @0x42eb60 loop over doRealDecode cases)
-int parse_record(const sq_ctx *c, const u8 *rec, u64 reclen, DecBlock &d) {
+// walk the tags of one block record (doDecode @0x42eb60 loop over doRealDecode cases): on the host for host buffers,
+// in k_parse_records for records that live on the device
+__host__ __device__ int parse_record(int md5, int lossy, const u8 *rec, u64 reclen, DecBlock &d) {
     const u8 *p = rec, *end = rec + reclen;
     u64 v;
     int k = get_vint(p, end, &v);
@@ -691,7 +692,7 @@ int parse_record(const sq_ctx *c, const u8 *rec, u64 reclen, DecBlock &d) {
         if (tag >= 32) continue;
         if (tag == 1) { if (sz != 4) return SQ_ERR_FORMAT; d.nreads = pay[0] | (pay[1] << 8) | (pay[2] << 16) | ((u32)pay[3] << 24); have_count = true; continue; }
         int mi = tag == 5 ? 0 : tag == 6 ? 1 : tag == 7 ? 2 : -1;
-        if (mi >= 0 && c->p.md5 && !(mi == 2 && c->p.lossy)) {
+        if (mi >= 0 && md5 && !(mi == 2 && lossy)) {
             if (sz < 16) return SQ_ERR_FORMAT;
             memcpy(d.md5[mi], pay, 16); d.has_md5[mi] = 1;
             pay += 16; sz -= 16;
@@ -711,10 +712,23 @@ int parse_record(const sq_ctx *c, const u8 *rec, u64 reclen, DecBlock &d) {
     return SQ_OK;
 }
 
-u32 rec_count(const u8 *rec, const DecBlock &d, int tag) {
+__host__ __device__ u32 rec_count(const u8 *rec, const DecBlock &d, int tag) {
     if (!d.len[tag]) return 0;
     const u8 *p = rec + d.off[tag];
     return p[0] | (p[1] << 8) | (p[2] << 16) | ((u32)p[3] << 24);
+}
+
+// one thread per device-resident record: its tag walk, and the two counts the host checks against the output capacity
+__global__ void k_parse_records(const u8 *const *recs, const u64 *lens, int n, int md5, int lossy, DecBlock *out, u32 *cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DecBlock d;
+    memset(&d, 0, sizeof d);
+    int r = parse_record(md5, lossy, recs[i], lens[i], d);
+    d.status = r;
+    cnt[2 * i] = r ? 0u : rec_count(recs[i], d, 14);
+    cnt[2 * i + 1] = r ? 0u : rec_count(recs[i], d, 26);
+    out[i] = d;
 }
 
 int decode_wave(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, sq_block_dec *out, bool host,
@@ -822,22 +836,40 @@ int decode_blocks(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, s
     c->timer.acc.clear();
     c->launches = 0;
     c->last_wave_blocks = 0;
-    // parse every record on the host; device-resident records are first copied back (headers are tiny
-    // but scattered, so the whole record is fetched -- the *_dev variant is a measurement aid)
+    // the tag walk of every record: on the host for host buffers, by one small kernel for device-resident records
+    // (only the parsed headers come back, not the records)
     std::vector<DecBlock> parsed(n);
-    std::vector<u8> tmp;
-    for (int i = 0; i < n; i++) {
-        memset(&parsed[i], 0, sizeof(DecBlock));
-        const u8 *hp = recs[i];
-        if (!host) {
-            tmp.resize(reclens[i]);
-            CUDA_OK(c, cudaMemcpy(tmp.data(), recs[i], reclens[i], cudaMemcpyDeviceToHost));
-            hp = tmp.data();
+    std::vector<u32> cnt(2 * (size_t)n);
+    if (host) {
+        for (int i = 0; i < n; i++) {
+            memset(&parsed[i], 0, sizeof(DecBlock));
+            int r = parse_record(c->p.md5, c->p.lossy, recs[i], reclens[i], parsed[i]);
+            parsed[i].status = r;
+            cnt[2 * i] = r ? 0u : rec_count(recs[i], parsed[i], 14);
+            cnt[2 * i + 1] = r ? 0u : rec_count(recs[i], parsed[i], 26);
         }
-        int r = parse_record(c, hp, reclens[i], parsed[i]);
-        if (r) parsed[i].status = r;
-        else if (parsed[i].nreads > out[i].readcap) parsed[i].status = SQ_ERR_CAPACITY;
-        else if (rec_count(hp, parsed[i], 14) > out[i].seqcap || rec_count(hp, parsed[i], 26) > out[i].seqcap) parsed[i].status = SQ_ERR_FORMAT;
+    } else {
+        Arena &A = c->arena;
+        A.reset();
+        const u8 **d_recs = (const u8 **)A.take(8 * (u64)n);
+        u64 *d_lens = (u64 *)A.take(8 * (u64)n);
+        DecBlock *d_parsed = (DecBlock *)A.take(sizeof(DecBlock) * (u64)n);
+        u32 *d_cnt = (u32 *)A.take(8 * (u64)n);
+        if (!d_recs || !d_lens || !d_parsed || !d_cnt) { c->err = "the device workspace is too small for the record headers"; return SQ_ERR_NOMEM; }
+        cudaStream_t st = c->stream;
+        CUDA_OK(c, cudaMemcpyAsync(d_recs, recs, 8 * (u64)n, cudaMemcpyHostToDevice, st));
+        CUDA_OK(c, cudaMemcpyAsync(d_lens, reclens, 8 * (u64)n, cudaMemcpyHostToDevice, st));
+        k_parse_records<<<(n + 63) / 64, 64, 0, st>>>(d_recs, d_lens, n, c->p.md5, c->p.lossy, d_parsed, d_cnt);
+        CUDA_OK(c, cudaGetLastError());
+        c->launches++;
+        CUDA_OK(c, cudaMemcpyAsync(parsed.data(), d_parsed, sizeof(DecBlock) * (u64)n, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(c, cudaMemcpyAsync(cnt.data(), d_cnt, 8 * (u64)n, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(c, cudaStreamSynchronize(st));
+    }
+    for (int i = 0; i < n; i++) {
+        if (parsed[i].status) continue;
+        if (parsed[i].nreads > out[i].readcap) parsed[i].status = SQ_ERR_CAPACITY;
+        else if (cnt[2 * i] > out[i].seqcap || cnt[2 * i + 1] > out[i].seqcap) parsed[i].status = SQ_ERR_FORMAT;
     }
     int worst = SQ_OK, i = 0;
     while (i < n) {
