@@ -294,6 +294,8 @@ SQ_D u32 wm_decode(u32 *mp, RcDecW &rc, int lane, u64 pol) {
 // Cumulative sums are absolute (they include the lower lanes), so the search needs no prefix: lane l "hits"
 // when code < c3_l * r, hits are monotone in l, and the symbol's lane is the number of lanes that miss.
 // The update adds 8 to every cumulative sum at or above the symbol -- one packed add per word.
+// In memory the words from SQ_QF on (the TAIL) hold their sums relative to the total of the words before them: see the
+// front / tail split below.
 struct RcWin;
 SQ_D u32 recip32(u32 d) { return 0xffffffffu / (d ? d : 1u); }     // in [2^32/d - 1, 2^32/d]: mulhi(n, .) is floor(n/d) or one less
 
