@@ -89,6 +89,10 @@ def lib():
             f.argtypes = [C.c_void_p, C.POINTER(CBlock), C.c_void_p]
         L.sqo_trace_stream.restype = C.c_int64
         L.sqo_trace_stream.argtypes = [C.c_void_p, C.POINTER(CBlock), C.c_int, C.c_void_p, C.c_void_p]
+        for n in ("sqo_small_encode", "sqo_small_decode"):
+            f = getattr(L, n)
+            f.restype = C.c_int64
+            f.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
         L.sqo_md5.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.sqo_rblock.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
         L.sqo_model_size.restype = C.c_uint64
@@ -179,6 +183,23 @@ def md5(data: bytes) -> bytes:
     out = np.zeros(16, np.uint8)
     lib().sqo_md5(a.ctypes.data if len(data) else None, len(data), out.ctypes.data)
     return out.tobytes()
+
+
+def small_encode(N: int, sym: np.ndarray) -> bytes:
+    """Range-coder bytes of `sym` through a fresh SIMPLE_MODEL<N> (aligned-mode side streams, compressOrder @0x424b70 ...)."""
+    sym = np.ascontiguousarray(sym, np.uint8)
+    out = np.empty(2 * sym.shape[0] + 64, np.uint8)
+    n = lib().sqo_small_encode(N, sym.ctypes.data if sym.shape[0] else None, sym.shape[0], out.ctypes.data)
+    assert n >= 0
+    return out[:n].tobytes()
+
+
+def small_decode(N: int, data: bytes, n: int) -> np.ndarray:
+    buf = np.frombuffer(data + bytes(16), np.uint8)
+    sym = np.empty(n, np.uint8)
+    r = lib().sqo_small_decode(N, buf.ctypes.data, n, sym.ctypes.data if n else None)
+    assert r >= 0
+    return sym
 
 
 def rblock(q: np.ndarray, r: float) -> np.ndarray:

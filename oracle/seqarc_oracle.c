@@ -514,6 +514,39 @@ static int64_t emit_small_sm(uint8_t *out, int tag, int N, const uint8_t *sym, u
     put_size(szslot, (uint64_t)(rc.out - p) + 4, 4);
     return rc.out - out;
 }
+/* Aligned-mode side streams (doAlignEncode @0x42d4c0): each is the bare range-coder output of a byte array through a
+ * fresh SIMPLE_MODEL<N> -- no count in front, the counts travel in their own tags (17 AlignCount membuf+0x30,
+ * 27 OrderCount +0xe8, 18 PosCount +0xf8, 19 CigalCount +0x108, 20 CigaVCount +0x138):
+ *   tag  8 Order  compressOrder          @0x424b70  N = 5   array membuf+0xe0, one symbol per read (loop count membuf+0x34)
+ *   tag 11 Pos    compressAlignInfo_Pos  @0x425d70  N = 2   array +0xf0, PosCount bits
+ *   tag 15 Mis    compressAlignInfo_Mis  @0x425ff0  N = 8 (SeqArcParam+0x1b60 in 1..7) or 9 (== 8), array +0x110, one per aligned read (+0x118)
+ *   tag 10 Rev    compressAlignInfo_Rev  @0x426480  N = 2   array +0x120, one per aligned read (+0x128)
+ *   tag 12 CigaL  compressAlignInfo_CigaL @0x426700 N = 2   array +0x100, CigalCount bits
+ *   tag 13 CigaV  compressAlignInfo_CigaV @0x426980 N = 4   array +0x130, CigaVCount symbols
+ * What the arrays MEAN (alignment, AlignInfoToSeq @0x42e020) is outside the hot path; these two functions restate the
+ * coders only and are pinned by decoding + re-encoding the streams of a reference-written aligned block. */
+int64_t sqo_small_encode(int N, const uint8_t *sym, uint32_t n, uint8_t *out) {
+    uint32_t m[SM_STRIDE(256)];
+    if (N < 2 || N > 256) return -1;
+    sm_init(m, N);
+    RC rc; rc_start_enc(&rc, out);
+    for (uint32_t i = 0; i < n; i++) {
+        if (sym[i] >= (uint32_t)N) return -1;
+        sm_encode(m, &rc, sym[i]);
+    }
+    rc_finish_enc(&rc);
+    return rc.out - out;
+}
+/* `in` must be followed by at least 8 readable bytes of slack (the decoder reads ahead) */
+int64_t sqo_small_decode(int N, const uint8_t *in, uint32_t n, uint8_t *sym) {
+    uint32_t m[SM_STRIDE(256)];
+    if (N < 2 || N > 256) return -1;
+    sm_init(m, N);
+    RC rc; rc_start_dec(&rc, in);
+    for (uint32_t i = 0; i < n; i++) sym[i] = (uint8_t)sm_decode(m, &rc);
+    return rc.in - in;
+}
+
 static int64_t emit_kmodel(sqo_ctx *c, uint8_t *out, int tag, const uint32_t *v, uint32_t n) {
     /* compressNDegeCnt @0x42d010 (tag 25), compressNDegePos @0x42d170 (tag 26) */
     if (n == 0) return 0;

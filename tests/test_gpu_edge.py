@@ -199,3 +199,21 @@ def test_corrupt_record_is_reported_not_crashed(fq):
     assert out[0].status in (-8, -9, -10, -6, -4)
     assert out[1].status == -6 and out[2].status == -6
     codec.close()
+
+
+def test_block_with_mapped_reads_is_refused_not_misdecoded(fq):
+    """Aligned-mode side streams are not coded by this path yet: a reference-written block that holds
+    mapped reads must come back SQ_ERR_FORMAT, next to an ordinary block that decodes."""
+    import os
+    from oracle import arcwalk
+    name = common.ALIGNED[0]
+    arc = arcwalk.parse_arc(open(os.path.join(common.GOLD, name + ".arc"), "rb").read())
+    aligned = arc["blocks"][0]["raw"]
+    codec = fq.EncapFqzComp(workspace_bytes=1 << 30)
+    good = ragged_block(12, 300)
+    mb = common.to_membuf(good)
+    codec.doFqzEncode([mb])
+    out = codec.doDecode([mb.out, aligned], raise_on_error=False)
+    assert out[0].status == 0 and out[0].seq.tobytes() == good.seq.tobytes()
+    assert out[1].status == -6
+    codec.close()

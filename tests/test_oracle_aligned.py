@@ -1,0 +1,54 @@
+"""Oracle vs a reference-written block that holds MAPPED reads: the coders of the aligned-mode side
+streams.  Each stream is the bare range-coder output of a byte array through a fresh SIMPLE_MODEL<N>
+(oracle/seqarc_oracle.c: sqo_small_encode / sqo_small_decode); the counts travel in their own tags.  Decoding a
+stream and coding it again must give back the reference's bytes.  (The CUDA path does not code these streams yet:
+DESIGN.md section 7.)"""
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from tests import common
+from oracle import arcwalk, pyoracle as po
+
+# tag -> (name, model size, which count)
+SIDE = {8: ("Order", 5, "order"), 11: ("Pos", 2, "pos"), 15: ("Mis", 8, "align"), 10: ("Rev", 2, "align"),
+        12: ("CigaL", 2, "cigal"), 13: ("CigaV", 4, "cigav")}
+
+
+@pytest.mark.parametrize("name", common.ALIGNED)
+def test_aligned_side_streams_decode_and_recode_to_the_reference_bytes(name):
+    m = common.MANIFEST[name]
+    data = open(os.path.join(common.GOLD, name + ".arc"), "rb").read()
+    assert hashlib.md5(data).hexdigest() == m["arc_md5"]
+    arc = arcwalk.parse_arc(data)
+    assert arc["trailer"][8].hex() == m["ref_md5"]                      # MD5 of the reference FASTA (SeqArcFile::writeMd5 @0x416ba0)
+    for blk in arc["blocks"]:
+        st = blk["streams"]
+        u32 = lambda t: struct.unpack("<I", st[t])[0]                   # noqa: E731
+        # compressReadCount / OrderCount / AlignCount / PosCount / CigalCount / CigaVCount @0x422a60-0x422b8f
+        cnt = {"reads": u32(1), "order": u32(27), "align": u32(17), "pos": u32(18), "cigal": u32(19), "cigav": u32(20)}
+        assert cnt["order"] == cnt["reads"] and 0 < cnt["align"] <= cnt["reads"]
+        sym = {}
+        for tag, (label, n_model, which) in SIDE.items():
+            sym[label] = po.small_decode(n_model, st[tag], cnt[which])
+            assert po.small_encode(n_model, sym[label]) == st[tag], label
+        # what the arrays say, as far as the coders' parity needs it: one Order symbol per read (0 = not mapped), one
+        # mismatch count and one strand flag per mapped read, one CigaV symbol (which of the three other bases) per mismatch
+        assert int((sym["Order"] == 0).sum()) == cnt["reads"] - cnt["align"]
+        assert int(sym["Mis"].astype(np.int64).sum()) == cnt["cigav"]
+        assert sym["CigaV"].max() <= 2
+        # the entropy-coded streams of the same block are still there: IDs, qualities, and the bases of the unmapped reads
+        assert all(t in st for t in (4, 5, 7, 6))
+
+
+def test_small_coder_round_trip_on_random_arrays():
+    rng = np.random.default_rng(5)
+    for n_model, n in ((2, 50000), (4, 3000), (5, 20000), (8, 1), (9, 70000), (2, 0)):
+        p = rng.dirichlet(np.ones(n_model) * 0.3)
+        a = rng.choice(n_model, n, p=p).astype(np.uint8)
+        enc = po.small_encode(n_model, a)
+        assert len(enc) >= 8
+        assert np.array_equal(po.small_decode(n_model, enc, n), a)

@@ -71,6 +71,10 @@ CASES = [
     # mate files of unequal size (trimmed reads): one file runs dry first, doReadPEJob keeps cutting until both do
     dict(name="illumina_pe_trim_blocks", src=dict(kind="illumina_pe_trim", n_templates=7000, seed=51), pe=True, opts=[],
          config={"BlockSize(M)": 1}),
+    # a block that DOES hold mapped reads: reads sampled from the reference FASTA itself, a tenth random.
+    # Pins the coders of the aligned-mode side streams (Order / Pos / Mis / Rev / CigaL / CigaV) for the oracle.
+    dict(name="aligned_se100", src="aligned", pe=False, opts=[], config=None, aligned=dict(n=200000, seed=11, reads=3000, L=100),
+         ref=dict(n=200000, seed=11)),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
@@ -80,6 +84,8 @@ def case_fastq(case):
     """FASTQ text of a case: (r1, r2) for PE, (r1,) for SE."""
     if case["src"] == "err":
         return tuple(gzip.open(os.path.join(GOLD, "err_pe1000_%d.fq.gz" % k), "rb").read() for k in (1, 2))
+    if case["src"] == "aligned":
+        return (aligned_reads(**case["aligned"])[1],)
     blk = sf.make_block(**case["src"])
     t = sf.to_fastq(blk)
     t = t if case["pe"] else (t,)
@@ -92,6 +98,33 @@ def plus_lines(text):
     for i in range(2, len(lines) - 1, 4):
         lines[i] = b"+" + lines[i - 2][1:]
     return b"\n".join(lines)
+
+
+def aligned_reads(n, seed, reads, L):
+    """(FASTA, FASTQ): one random chromosome and single-end reads sampled from it -- 0..2 substitutions each, half of them
+    reverse-complemented, a tenth of the reads random (they stay unmapped).  One generator draws the reference first."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref = acgt[rng.integers(0, 4, n)]
+    fa = b">chr1\n" + b"".join(ref[i:i + 60].tobytes() + b"\n" for i in range(0, n, 60))
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    recs = []
+    for i in range(reads):
+        kind = rng.random()
+        if kind < 0.1:
+            s = acgt[rng.integers(0, 4, L)]
+        else:
+            p = int(rng.integers(0, n - L))
+            s = ref[p:p + L].copy()
+            for _ in range(int(rng.integers(0, 3))):
+                k = int(rng.integers(0, L))
+                s[k] = acgt[rng.integers(0, 4)]
+            if rng.random() < 0.5:
+                s = np.array([comp[int(c)] for c in s[::-1]], np.uint8)
+        q = (np.clip(np.rint(rng.normal(30, 6, L)), 2, 40).astype(np.uint8) + 33)
+        recs.append(b"@r%d\n" % i + s.tobytes() + b"\n+\n" + q.tobytes() + b"\n")
+    return fa, b"".join(recs)
 
 
 def random_reference(n, seed):
@@ -130,7 +163,7 @@ def main():
             args = ["-c", "-t", "1", "-f"] + case["opts"]
             ref_md5 = None
             if case.get("ref"):     # `SeqArc -i` writes a ~2 GB hash index beside the FASTA (temporary)
-                fa = random_reference(**case["ref"])
+                fa = aligned_reads(**case["aligned"])[0] if case.get("aligned") else random_reference(**case["ref"])
                 open(os.path.join(tmp, "ref.fa"), "wb").write(fa)
                 rc, log = po.run_ref(["-i", "ref.fa"], tmp)
                 assert rc == 0, log[-2000:]
@@ -145,7 +178,9 @@ def main():
             rc, log = po.run_ref(args, tmp, lossy_shim=case.get("shim", False), config=case["config"],
                                  fake_size=case.get("fake_size"))
             assert rc == 0, (case["name"], rc, log[-2000:])
-            if case.get("ref"):
+            if case.get("aligned"):
+                assert "Align block:1" in log, log[-1500:]
+            elif case.get("ref"):
                 assert "Align block:0" in log, log[-1500:]
             arc = open(os.path.join(tmp, "out.arc"), "rb").read()
             entry = dict(src=case["src"], pe=case["pe"], opts=case["opts"], config=case["config"],
@@ -153,6 +188,8 @@ def main():
                          fastq_md5=[hashlib.md5(t).hexdigest() for t in fq])
             if ref_md5:
                 entry.update(ref=case["ref"], ref_md5=ref_md5)
+            if case.get("aligned"):
+                entry.update(aligned=case["aligned"])
             if case.get("plus"):
                 entry.update(plus=True)
             if case.get("fake_size"):
