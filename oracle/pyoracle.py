@@ -93,6 +93,8 @@ def lib():
             f = getattr(L, n)
             f.restype = C.c_int64
             f.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.sqo_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.sqo_set_reference.restype = None
         L.sqo_md5.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.sqo_rblock.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
         L.sqo_model_size.restype = C.c_uint64
@@ -161,6 +163,13 @@ class Oracle:
         got = lib().sqo_save_model(self.h, buf.ctypes.data)
         assert got == n
         return buf.tobytes()
+
+    def set_reference(self, fasta: bytes):
+        """Aligned mode (decode, single-end): the reference FASTA the archive was written against; header lines dropped, the
+        sequences concatenated."""
+        seq = b"".join(l for l in fasta.split(b"\n") if l and not l.startswith(b">"))
+        self._ref = np.frombuffer(seq, np.uint8).copy()
+        lib().sqo_set_reference(self.h, self._ref.ctypes.data, self._ref.shape[0])
 
     def decode_block(self, rec: bytes, idcap=None, seqcap=None, readcap=None, longflag=0) -> Block:
         rec_a = np.frombuffer(rec, dtype=np.uint8)

@@ -169,6 +169,11 @@ struct sqo_ctx {
     uint8_t *d_tip, *d_ch, *d_maxq;
     uint32_t *d_cnt, *d_pos;
     uint32_t n_tip, n_ch, n_maxq, n_cnt, n_pos;
+    /* aligned mode (decode only, single-end): the reference sequence and the side arrays of the block (membuf+0xe0..0x138) */
+    const uint8_t *ref; uint64_t reflen;
+    uint8_t *a_order, *a_pos, *a_mis, *a_rev, *a_cigal, *a_cigav;
+    uint32_t n_order, n_align, n_posbits, n_cigal, n_cigav;
+    uint32_t al_i, al_pos, al_cigal, al_cigav;      /* cursors: this+0x1758, +0x1718, +0x1720, +0x175c */
 };
 
 static void init_tables(void) {
@@ -201,6 +206,7 @@ void sqo_destroy(sqo_ctx *c) {
     if (!c) return;
     free(c->seqtab); free(c->qual); free(c->name_prefix); free(c->name_suffix); free(c->name_len);
     free(c->name_middle); free(c->d_tip); free(c->d_ch); free(c->d_maxq); free(c->d_cnt); free(c->d_pos);
+    free(c->a_order); free(c->a_pos); free(c->a_mis); free(c->a_rev); free(c->a_cigal); free(c->a_cigav);
     free(c);
 }
 

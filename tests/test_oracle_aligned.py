@@ -1,8 +1,10 @@
-"""Oracle vs a reference-written block that holds MAPPED reads: the coders of the aligned-mode side
-streams.  Each stream is the bare range-coder output of a byte array through a fresh SIMPLE_MODEL<N>
-(oracle/seqarc_oracle.c: sqo_small_encode / sqo_small_decode); the counts travel in their own tags.  Decoding a
-stream and coding it again must give back the reference's bytes.  (The CUDA path does not code these streams yet:
-DESIGN.md section 7.)"""
+"""Oracle vs reference-written blocks that hold MAPPED reads (single-end).
+  * the coders of the aligned-mode side streams: each stream is the bare range-coder output of a byte array through a fresh
+    SIMPLE_MODEL<N> (oracle/seqarc_oracle.c: sqo_small_encode / sqo_small_decode), the counts travel in their own tags;
+    decoding a stream and coding it again must give back the reference's bytes;
+  * the decode side as a whole (doAlignDecode @0x42c8d0): with the reference sequence the oracle rebuilds every mapped read
+    (getRealPos @0x42de30, AlignInfoToSeq @0x42e020) and gives back the input FASTQ, degenerate bases included.
+(The CUDA path does not code these streams yet: DESIGN.md section 7.)"""
 import hashlib
 import os
 import struct
@@ -39,9 +41,32 @@ def test_aligned_side_streams_decode_and_recode_to_the_reference_bytes(name):
         # mismatch count and one strand flag per mapped read, one CigaV symbol (which of the three other bases) per mismatch
         assert int((sym["Order"] == 0).sum()) == cnt["reads"] - cnt["align"]
         assert int(sym["Mis"].astype(np.int64).sum()) == cnt["cigav"]
-        assert sym["CigaV"].max() <= 2
+        assert sym["CigaV"].max() <= 3                                  # 3 = the read has N where the reference has a base
+        assert cnt["pos"] % cnt["align"] == 0                           # single-end: the same number of position bits per mapped read
         # the entropy-coded streams of the same block are still there: IDs, qualities, and the bases of the unmapped reads
         assert all(t in st for t in (4, 5, 7, 6))
+
+
+@pytest.mark.parametrize("name", common.ALIGNED)
+def test_oracle_decodes_the_aligned_block_back_to_the_input(name):
+    from tools import make_golden as mg
+    m = common.MANIFEST[name]
+    fasta, fastq = mg.aligned_reads(**m["aligned"])
+    assert hashlib.md5(fastq).hexdigest() == m["fastq_md5"][0] and hashlib.md5(fasta).hexdigest() == m["ref_md5"]
+    arc = arcwalk.parse_arc(open(os.path.join(common.GOLD, name + ".arc"), "rb").read())
+    want = po.block_from_fastq(fastq)
+    o = po.Oracle(md5=1)
+    with pytest.raises(RuntimeError):                       # mapped reads cannot be rebuilt without the reference
+        o.decode_block(arc["blocks"][0]["raw"])
+    o.set_reference(fasta)
+    got = o.decode_block(arc["blocks"][0]["raw"])
+    assert np.array_equal(got.seqlen, want.seqlen) and np.array_equal(got.idlen, want.idlen)
+    assert got.ids.tobytes() == want.ids.tobytes() and got.qual.tobytes() == want.qual.tobytes()
+    assert got.seq.tobytes() == want.seq.tobytes()
+    st = arc["blocks"][0]["streams"]
+    assert st[6][:16] == po.md5(want.seq.tobytes())          # the block's base MD5 covers mapped and unmapped reads alike
+    mapped = struct.unpack("<I", st[17])[0]
+    assert 0 < mapped < want.seqlen.size                     # both kinds of read are in the block
 
 
 def test_small_coder_round_trip_on_random_arrays():

@@ -75,6 +75,8 @@ CASES = [
     # Pins the coders of the aligned-mode side streams (Order / Pos / Mis / Rev / CigaL / CigaV) for the oracle.
     dict(name="aligned_se100", src="aligned", pe=False, opts=[], config=None, aligned=dict(n=200000, seed=11, reads=3000, L=100),
          ref=dict(n=200000, seed=11)),
+    dict(name="aligned_se_var", src="aligned", pe=False, opts=[], config=None,
+         aligned=dict(n=1000000, seed=12, reads=2500, L=150, Lmin=60, n_rate=0.004), ref=dict(n=1000000, seed=12)),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
@@ -100,9 +102,10 @@ def plus_lines(text):
     return b"\n".join(lines)
 
 
-def aligned_reads(n, seed, reads, L):
+def aligned_reads(n, seed, reads, L, Lmin=None, n_rate=0.0):
     """(FASTA, FASTQ): one random chromosome and single-end reads sampled from it -- 0..2 substitutions each, half of them
-    reverse-complemented, a tenth of the reads random (they stay unmapped).  One generator draws the reference first."""
+    reverse-complemented, a tenth of the reads random (they stay unmapped).  One generator draws the reference first.
+    Lmin: read lengths uniform in [Lmin, L]; n_rate: bases turned into N with quality '#' (degenerate-base overlay)."""
     import numpy as np
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", np.uint8)
@@ -110,7 +113,10 @@ def aligned_reads(n, seed, reads, L):
     fa = b">chr1\n" + b"".join(ref[i:i + 60].tobytes() + b"\n" for i in range(0, n, 60))
     comp = {65: 84, 67: 71, 71: 67, 84: 65}
     recs = []
+    Lmax = L
     for i in range(reads):
+        if Lmin is not None:
+            L = int(rng.integers(Lmin, Lmax + 1))
         kind = rng.random()
         if kind < 0.1:
             s = acgt[rng.integers(0, 4, L)]
@@ -123,6 +129,10 @@ def aligned_reads(n, seed, reads, L):
             if rng.random() < 0.5:
                 s = np.array([comp[int(c)] for c in s[::-1]], np.uint8)
         q = (np.clip(np.rint(rng.normal(30, 6, L)), 2, 40).astype(np.uint8) + 33)
+        if n_rate:
+            nm = rng.random(L) < n_rate
+            s = np.where(nm, ord("N"), s).astype(np.uint8)
+            q = np.where(nm, ord("#"), q).astype(np.uint8)
         recs.append(b"@r%d\n" % i + s.tobytes() + b"\n+\n" + q.tobytes() + b"\n")
     return fa, b"".join(recs)
 
