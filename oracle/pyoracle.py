@@ -93,6 +93,11 @@ def lib():
             f = getattr(L, n)
             f.restype = C.c_int64
             f.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.sqo_set_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                    C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.sqo_set_align.restype = None
+        L.sqo_get_align.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.sqo_get_align.restype = C.c_uint32
         L.sqo_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.sqo_set_reference.restype = None
         L.sqo_md5.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
@@ -170,6 +175,23 @@ class Oracle:
         seq = b"".join(l for l in fasta.split(b"\n") if l and not l.startswith(b">"))
         self._ref = np.frombuffer(seq, np.uint8).copy()
         lib().sqo_set_reference(self.h, self._ref.ctypes.data, self._ref.shape[0])
+
+    def align_arrays(self):
+        """Side arrays of the aligned block decoded last: dict(order, pos, mis, rev, cigal, cigav) of uint8 arrays."""
+        out = {}
+        for k, name in enumerate(("order", "pos", "mis", "rev", "cigal", "cigav")):
+            ptr = C.c_void_p()
+            n = lib().sqo_get_align(self.h, k, C.byref(ptr))
+            out[name] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (n,)).copy() if n else np.zeros(0, np.uint8)
+        return out
+
+    def set_align(self, a):
+        """The aligner's arrays for the next encode_block call (ref_mode = 1, single-end); None clears them."""
+        self._al = {k: np.ascontiguousarray(v, np.uint8) for k, v in (a or {}).items()}
+        g = lambda k: self._al[k].ctypes.data if a and self._al[k].shape[0] else None      # noqa: E731
+        n = lambda k: int(self._al[k].shape[0]) if a else 0                               # noqa: E731
+        lib().sqo_set_align(self.h, g("order"), g("pos"), n("pos"), g("mis"), g("rev"), n("mis"), g("cigal"), n("cigal"),
+                            g("cigav"), n("cigav"))
 
     def decode_block(self, rec: bytes, idcap=None, seqcap=None, readcap=None, longflag=0) -> Block:
         rec_a = np.frombuffer(rec, dtype=np.uint8)

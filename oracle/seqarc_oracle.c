@@ -174,6 +174,9 @@ struct sqo_ctx {
     uint8_t *a_order, *a_pos, *a_mis, *a_rev, *a_cigal, *a_cigav;
     uint32_t n_order, n_align, n_posbits, n_cigal, n_cigav;
     uint32_t al_i, al_pos, al_cigal, al_cigav;      /* cursors: this+0x1758, +0x1718, +0x1720, +0x175c */
+    /* encode side: the aligner's arrays for the NEXT sqo_encode_block call (sqo_set_align; the caller keeps them alive) */
+    const uint8_t *e_order, *e_pos, *e_mis, *e_rev, *e_cigal, *e_cigav;
+    uint32_t e_align, e_posbits, e_ncigal, e_ncigav;
 };
 
 static void init_tables(void) {
@@ -621,6 +624,32 @@ static int put_count(uint8_t *p, int tag, uint32_t v) {
     p[n] = 0x84; put_u32le(p + n + 1, v);
     return n + 5;
 }
+static int64_t put_side(uint8_t *p, int tag, int N, const uint8_t *sym, uint32_t n) {   /* "tag | size(4) | RC bytes" */
+    int k = put_id(p, (uint64_t)tag);
+    int64_t len = sqo_small_encode(N, sym, n, p + k + 4);
+    put_size(p + k, (uint64_t)len, 4);
+    return k + 4 + len;
+}
+/* Aligned mode, encode side, single-end (doAlignEncode @0x42d4c0): what the aligner found for the block the next
+ * sqo_encode_block call codes -- order[nreads] (0 = not mapped), n_posbits position bits, mis[n_align], rev[n_align],
+ * n_cigal offset bits, cigav[n_cigav].  The arrays' meaning: seqarc_oracle_dec.inc (align_to_seq).  n_align = 0 clears. */
+void sqo_set_align(sqo_ctx *c, const uint8_t *order, const uint8_t *pos, uint32_t n_posbits, const uint8_t *mis, const uint8_t *rev,
+                   uint32_t n_align, const uint8_t *cigal, uint32_t n_cigal, const uint8_t *cigav, uint32_t n_cigav) {
+    c->e_order = order; c->e_pos = pos; c->e_mis = mis; c->e_rev = rev; c->e_cigal = cigal; c->e_cigav = cigav;
+    c->e_posbits = n_posbits; c->e_align = n_align; c->e_ncigal = n_cigal; c->e_ncigav = n_cigav;
+}
+/* the side arrays of the block sqo_decode_block decoded last: which = 0 order, 1 pos bits, 2 mis, 3 rev, 4 cigal bits, 5 cigav */
+uint32_t sqo_get_align(const sqo_ctx *c, int which, const uint8_t **arr) {
+    switch (which) {
+    case 0: *arr = c->a_order; return c->n_order;
+    case 1: *arr = c->a_pos; return c->n_posbits;
+    case 2: *arr = c->a_mis; return c->n_align;
+    case 3: *arr = c->a_rev; return c->n_align;
+    case 4: *arr = c->a_cigal; return c->n_cigal;
+    case 5: *arr = c->a_cigav; return c->n_cigav;
+    }
+    *arr = 0; return 0;
+}
 static int put_empty_rc(uint8_t *p, int tag) {
     int n = put_id(p, (uint64_t)tag);
     put_size(p + n, 8, 4);
@@ -649,9 +678,13 @@ int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t 
     p += put_id(p, 1); *p++ = 0x84; put_u32le(p, b->nreads); p += 4;
     /* Len: tag 4 */
     { p += put_id(p, 4); uint8_t *s = p; p += 4; int64_t n = sqo_stream_len(c, b, p); put_size(s, n, 4); p += n; }
-    if (c->p.ref_mode) {                                              /* @0x42d547-0x42d56f */
+    const int aligned = c->p.ref_mode == 1 && c->e_align > 0;         /* this block holds mapped reads (single-end) */
+    if (aligned) {                                                    /* every read was handed to the aligner */
+        p += put_count(p, 27, b->nreads);
+        p += put_side(p, 8, 5, c->e_order, b->nreads);                /* compressOrder @0x424b70 */
+    } else if (c->p.ref_mode) {                                       /* @0x42d547-0x42d56f */
         p += put_count(p, 27, sqo_tested_reads(b->nreads, c->p.ref_mode == 2));
-        p += put_empty_rc(p, 8);                                      /* compressOrder @0x424b70 */
+        p += put_empty_rc(p, 8);
     }
     /* ID: tag 5 (compressID @0x4247c0) */
     {
@@ -670,7 +703,15 @@ int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t 
         p += sqo_stream_qual(c, b, p);
         put_size(s, p - st, 4);
     }
-    if (c->p.ref_mode) {                                              /* @0x42d5bd-0x42d6c7, PE part @0x42d830 */
+    if (aligned) {
+        p += put_count(p, 17, c->e_align); p += put_count(p, 18, c->e_posbits);
+        p += put_count(p, 19, c->e_ncigal); p += put_count(p, 20, c->e_ncigav);
+        p += put_side(p, 11, 2, c->e_pos, c->e_posbits);              /* compressAlignInfo_Pos @0x425d70 */
+        p += put_side(p, 15, 8, c->e_mis, c->e_align);                /* ..._Mis @0x425ff0 (N = 9 when SeqArcParam+0x1b60 == 8) */
+        p += put_side(p, 10, 2, c->e_rev, c->e_align);                /* ..._Rev @0x426480 */
+        p += put_side(p, 12, 2, c->e_cigal, c->e_ncigal);             /* ..._CigaL @0x426700 */
+        p += put_side(p, 13, 4, c->e_cigav, c->e_ncigav);             /* ..._CigaV @0x426980 */
+    } else if (c->p.ref_mode) {                                       /* @0x42d5bd-0x42d6c7, PE part @0x42d830 */
         for (int t = 17; t <= 20; t++) p += put_count(p, t, 0);
         if (c->p.ref_mode == 2) {
             p += put_count(p, 21, 9);                                 /* membuf+0x28: 9 on every PE archive observed */
@@ -690,7 +731,15 @@ int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t 
     {
         p += put_id(p, 6); uint8_t *s = p; p += 4; uint8_t *st = p;
         if (c->p.md5) { memcpy(p, md5[1], 16); p += 16; }
-        p += sqo_stream_seq(c, b, p);
+        if (aligned) {                                                /* only the reads the aligner left unmapped are coded */
+            RC rc; rc_start_enc(&rc, p);
+            reset_seq_model(c);
+            const uint8_t *q = b->seq;
+            for (uint32_t i = 0; i < b->nreads; i++) { if (!c->e_order[i]) encode_seq(c, &rc, q, b->seqlen[i], 0); q += b->seqlen[i]; }
+            rc_finish_enc(&rc);
+            p = rc.out;
+        } else
+            p += sqo_stream_seq(c, b, p);
         put_size(s, p - st, 4);
     }
     put_size(blkslot, (uint64_t)(p - blkslot - 4), 4);

@@ -3,7 +3,8 @@
     SIMPLE_MODEL<N> (oracle/seqarc_oracle.c: sqo_small_encode / sqo_small_decode), the counts travel in their own tags;
     decoding a stream and coding it again must give back the reference's bytes;
   * the decode side as a whole (doAlignDecode @0x42c8d0): with the reference sequence the oracle rebuilds every mapped read
-    (getRealPos @0x42de30, AlignInfoToSeq @0x42e020) and gives back the input FASTQ, degenerate bases included.
+    (getRealPos @0x42de30, AlignInfoToSeq @0x42e020) and gives back the input FASTQ, degenerate bases included;
+  * the encode side given the aligner's arrays (doAlignEncode @0x42d4c0): the whole record, byte for byte.
 (The CUDA path does not code these streams yet: DESIGN.md section 7.)"""
 import hashlib
 import os
@@ -67,6 +68,28 @@ def test_oracle_decodes_the_aligned_block_back_to_the_input(name):
     assert st[6][:16] == po.md5(want.seq.tobytes())          # the block's base MD5 covers mapped and unmapped reads alike
     mapped = struct.unpack("<I", st[17])[0]
     assert 0 < mapped < want.seqlen.size                     # both kinds of read are in the block
+
+
+@pytest.mark.parametrize("name", common.ALIGNED)
+def test_oracle_encodes_the_aligned_block_from_the_aligners_arrays(name):
+    """Encode side (doAlignEncode @0x42d4c0): the input block plus what the aligner found -- taken from the decoded golden,
+    the aligner itself is outside the path -- must give the reference's whole record: side streams, counts, Dege streams over
+    all reads, and a base stream that codes the unmapped reads only."""
+    from tools import make_golden as mg
+    m = common.MANIFEST[name]
+    fasta, fastq = mg.aligned_reads(**m["aligned"])
+    rec = arcwalk.parse_arc(open(os.path.join(common.GOLD, name + ".arc"), "rb").read())["blocks"][0]["raw"]
+    d = po.Oracle(md5=1)
+    d.set_reference(fasta)
+    d.decode_block(rec)
+    arrays = d.align_arrays()
+    e = po.Oracle(md5=1, ref_mode=1)
+    e.set_align(arrays)
+    blk = po.block_from_fastq(fastq)
+    assert e.encode_block(blk) == rec
+    e.set_align(None)                                        # without them the same call writes the nothing-mapped framing
+    plain = e.encode_block(blk)
+    assert plain != rec and po.Oracle(md5=1).decode_block(plain).seq.tobytes() == blk.seq.tobytes()
 
 
 def test_small_coder_round_trip_on_random_arrays():
