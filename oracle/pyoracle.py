@@ -96,6 +96,8 @@ def lib():
         L.sqo_set_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                     C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.sqo_set_align.restype = None
+        L.sqo_set_align_pe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.sqo_set_align_pe.restype = None
         L.sqo_get_align.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.sqo_get_align.restype = C.c_uint32
         L.sqo_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -179,15 +181,19 @@ class Oracle:
     def align_arrays(self):
         """Side arrays of the aligned block decoded last: dict(order, pos, mis, rev, cigal, cigav) of uint8 arrays."""
         out = {}
-        for k, name in enumerate(("order", "pos", "mis", "rev", "cigal", "cigav")):
+        for k, name in enumerate(("order", "pos", "mis", "rev", "cigal", "cigav", "perel")):
             ptr = C.c_void_p()
             n = lib().sqo_get_align(self.h, k, C.byref(ptr))
             out[name] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (n,)).copy() if n else np.zeros(0, np.uint8)
+        out["insbits"] = int(lib().sqo_get_align(self.h, 7, C.byref(C.c_void_p())))      # paired-end: PEInsrNum
         return out
 
     def set_align(self, a):
         """The aligner's arrays for the next encode_block call (ref_mode = 1, single-end); None clears them."""
-        self._al = {k: np.ascontiguousarray(v, np.uint8) for k, v in (a or {}).items()}
+        self._al = {k: np.ascontiguousarray(v, np.uint8) for k, v in (a or {}).items() if k != "insbits"}
+        pe = self._al.get("perel")
+        lib().sqo_set_align_pe(self.h, pe.ctypes.data if pe is not None and pe.shape[0] else None,
+                               int(pe.shape[0]) if pe is not None else 0, int((a or {}).get("insbits", 0)))
         g = lambda k: self._al[k].ctypes.data if a and self._al[k].shape[0] else None      # noqa: E731
         n = lambda k: int(self._al[k].shape[0]) if a else 0                               # noqa: E731
         lib().sqo_set_align(self.h, g("order"), g("pos"), n("pos"), g("mis"), g("rev"), n("mis"), g("cigal"), n("cigal"),

@@ -174,9 +174,12 @@ struct sqo_ctx {
     uint8_t *a_order, *a_pos, *a_mis, *a_rev, *a_cigal, *a_cigav;
     uint32_t n_order, n_align, n_posbits, n_cigal, n_cigav;
     uint32_t al_i, al_pos, al_cigal, al_cigav;      /* cursors: this+0x1758, +0x1718, +0x1720, +0x175c */
+    uint8_t *a_perel; uint32_t n_perel, n_insbits, al_perel;   /* paired-end: PERelation array (membuf+0x140), PEInsrNum (+0x28), cursor this+0x1764 */
+    uint64_t al_cur;                                 /* this+0x1710: the position computed last */
     /* encode side: the aligner's arrays for the NEXT sqo_encode_block call (sqo_set_align; the caller keeps them alive) */
     const uint8_t *e_order, *e_pos, *e_mis, *e_rev, *e_cigal, *e_cigav;
     uint32_t e_align, e_posbits, e_ncigal, e_ncigav;
+    const uint8_t *e_perel; uint32_t e_nperel, e_insbits;     /* paired-end (sqo_set_align_pe) */
 };
 
 static void init_tables(void) {
@@ -209,7 +212,7 @@ void sqo_destroy(sqo_ctx *c) {
     if (!c) return;
     free(c->seqtab); free(c->qual); free(c->name_prefix); free(c->name_suffix); free(c->name_len);
     free(c->name_middle); free(c->d_tip); free(c->d_ch); free(c->d_maxq); free(c->d_cnt); free(c->d_pos);
-    free(c->a_order); free(c->a_pos); free(c->a_mis); free(c->a_rev); free(c->a_cigal); free(c->a_cigav);
+    free(c->a_perel); free(c->a_order); free(c->a_pos); free(c->a_mis); free(c->a_rev); free(c->a_cigal); free(c->a_cigav);
     free(c);
 }
 
@@ -647,8 +650,14 @@ uint32_t sqo_get_align(const sqo_ctx *c, int which, const uint8_t **arr) {
     case 3: *arr = c->a_rev; return c->n_align;
     case 4: *arr = c->a_cigal; return c->n_cigal;
     case 5: *arr = c->a_cigav; return c->n_cigav;
+    case 6: *arr = c->a_perel; return c->n_perel;
+    case 7: *arr = 0; return c->n_insbits;
     }
     *arr = 0; return 0;
+}
+/* paired-end part: PERelation symbols of the pairs with both mates mapped, and PEInsrNum (membuf+0x28) */
+void sqo_set_align_pe(sqo_ctx *c, const uint8_t *perel, uint32_t n_perel, uint32_t insbits) {
+    c->e_perel = perel; c->e_nperel = n_perel; c->e_insbits = insbits;
 }
 static int put_empty_rc(uint8_t *p, int tag) {
     int n = put_id(p, (uint64_t)tag);
@@ -678,7 +687,7 @@ int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t 
     p += put_id(p, 1); *p++ = 0x84; put_u32le(p, b->nreads); p += 4;
     /* Len: tag 4 */
     { p += put_id(p, 4); uint8_t *s = p; p += 4; int64_t n = sqo_stream_len(c, b, p); put_size(s, n, 4); p += n; }
-    const int aligned = c->p.ref_mode == 1 && c->e_align > 0;         /* this block holds mapped reads (single-end) */
+    const int aligned = c->p.ref_mode && c->e_align > 0;              /* this block holds mapped reads */
     if (aligned) {                                                    /* every read was handed to the aligner */
         p += put_count(p, 27, b->nreads);
         p += put_side(p, 8, 5, c->e_order, b->nreads);                /* compressOrder @0x424b70 */
@@ -706,6 +715,10 @@ int64_t sqo_encode_block(sqo_ctx *c, const sqo_block *b, uint8_t *out, uint64_t 
     if (aligned) {
         p += put_count(p, 17, c->e_align); p += put_count(p, 18, c->e_posbits);
         p += put_count(p, 19, c->e_ncigal); p += put_count(p, 20, c->e_ncigav);
+        if (c->p.ref_mode == 2) {
+            p += put_count(p, 21, c->e_insbits); p += put_count(p, 22, c->e_nperel);
+            p += put_side(p, 9, 4, c->e_perel, c->e_nperel);          /* compressPERelation @0x422be0 */
+        }
         p += put_side(p, 11, 2, c->e_pos, c->e_posbits);              /* compressAlignInfo_Pos @0x425d70 */
         p += put_side(p, 15, 8, c->e_mis, c->e_align);                /* ..._Mis @0x425ff0 (N = 9 when SeqArcParam+0x1b60 == 8) */
         p += put_side(p, 10, 2, c->e_rev, c->e_align);                /* ..._Rev @0x426480 */

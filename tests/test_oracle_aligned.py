@@ -1,4 +1,4 @@
-"""Oracle vs reference-written blocks that hold MAPPED reads (single-end).
+"""Oracle vs reference-written blocks that hold MAPPED reads, single- and paired-end.
   * the coders of the aligned-mode side streams: each stream is the bare range-coder output of a byte array through a fresh
     SIMPLE_MODEL<N> (oracle/seqarc_oracle.c: sqo_small_encode / sqo_small_decode), the counts travel in their own tags;
     decoding a stream and coding it again must give back the reference's bytes;
@@ -19,6 +19,13 @@ from oracle import arcwalk, pyoracle as po
 # tag -> (name, model size, which count)
 SIDE = {8: ("Order", 5, "order"), 11: ("Pos", 2, "pos"), 15: ("Mis", 8, "align"), 10: ("Rev", 2, "align"),
         12: ("CigaL", 2, "cigal"), 13: ("CigaV", 4, "cigav")}
+
+
+def _inputs(name):
+    """(reference FASTA, (FASTQ, ...)) of an aligned golden, rebuilt by the seeded generator that made it."""
+    from tools import make_golden as mg
+    m = common.MANIFEST[name]
+    return mg.aligned_case(dict(pe=m["pe"], aligned=m["aligned"]))
 
 
 @pytest.mark.parametrize("name", common.ALIGNED)
@@ -43,19 +50,23 @@ def test_aligned_side_streams_decode_and_recode_to_the_reference_bytes(name):
         assert int((sym["Order"] == 0).sum()) == cnt["reads"] - cnt["align"]
         assert int(sym["Mis"].astype(np.int64).sum()) == cnt["cigav"]
         assert sym["CigaV"].max() <= 3                                  # 3 = the read has N where the reference has a base
-        assert cnt["pos"] % cnt["align"] == 0                           # single-end: the same number of position bits per mapped read
+        if not m["pe"]:
+            assert cnt["pos"] % cnt["align"] == 0                       # single-end: the same number of position bits per mapped read
+        else:                                                           # compressPERelation @0x422be0: one symbol per pair mapped with both mates
+            n_rel = u32(22)
+            rel = po.small_decode(4, st[9], n_rel)
+            assert po.small_encode(4, rel) == st[9] and 0 < n_rel <= cnt["align"] // 2
         # the entropy-coded streams of the same block are still there: IDs, qualities, and the bases of the unmapped reads
         assert all(t in st for t in (4, 5, 7, 6))
 
 
 @pytest.mark.parametrize("name", common.ALIGNED)
 def test_oracle_decodes_the_aligned_block_back_to_the_input(name):
-    from tools import make_golden as mg
     m = common.MANIFEST[name]
-    fasta, fastq = mg.aligned_reads(**m["aligned"])
-    assert hashlib.md5(fastq).hexdigest() == m["fastq_md5"][0] and hashlib.md5(fasta).hexdigest() == m["ref_md5"]
+    fasta, fastq = _inputs(name)
+    assert [hashlib.md5(t).hexdigest() for t in fastq] == m["fastq_md5"] and hashlib.md5(fasta).hexdigest() == m["ref_md5"]
     arc = arcwalk.parse_arc(open(os.path.join(common.GOLD, name + ".arc"), "rb").read())
-    want = po.block_from_fastq(fastq)
+    want = po.block_from_fastq(*fastq)
     o = po.Oracle(md5=1)
     with pytest.raises(RuntimeError):                       # mapped reads cannot be rebuilt without the reference
         o.decode_block(arc["blocks"][0]["raw"])
@@ -75,17 +86,16 @@ def test_oracle_encodes_the_aligned_block_from_the_aligners_arrays(name):
     """Encode side (doAlignEncode @0x42d4c0): the input block plus what the aligner found -- taken from the decoded golden,
     the aligner itself is outside the path -- must give the reference's whole record: side streams, counts, Dege streams over
     all reads, and a base stream that codes the unmapped reads only."""
-    from tools import make_golden as mg
     m = common.MANIFEST[name]
-    fasta, fastq = mg.aligned_reads(**m["aligned"])
+    fasta, fastq = _inputs(name)
     rec = arcwalk.parse_arc(open(os.path.join(common.GOLD, name + ".arc"), "rb").read())["blocks"][0]["raw"]
     d = po.Oracle(md5=1)
     d.set_reference(fasta)
     d.decode_block(rec)
     arrays = d.align_arrays()
-    e = po.Oracle(md5=1, ref_mode=1)
+    e = po.Oracle(md5=1, ref_mode=2 if m["pe"] else 1)
     e.set_align(arrays)
-    blk = po.block_from_fastq(fastq)
+    blk = po.block_from_fastq(*fastq)
     assert e.encode_block(blk) == rec
     e.set_align(None)                                        # without them the same call writes the nothing-mapped framing
     plain = e.encode_block(blk)

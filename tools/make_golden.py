@@ -77,6 +77,8 @@ CASES = [
          ref=dict(n=200000, seed=11)),
     dict(name="aligned_se_var", src="aligned", pe=False, opts=[], config=None,
          aligned=dict(n=1000000, seed=12, reads=2500, L=150, Lmin=60, n_rate=0.004), ref=dict(n=1000000, seed=12)),
+    dict(name="aligned_pe100", src="aligned", pe=True, opts=[], config=None, aligned=dict(n=300000, seed=21, pairs=2000, L=100),
+         ref=dict(n=300000, seed=21)),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
          config={"Qlevel": 3, "Slevel": 2}),
 ]
@@ -87,7 +89,7 @@ def case_fastq(case):
     if case["src"] == "err":
         return tuple(gzip.open(os.path.join(GOLD, "err_pe1000_%d.fq.gz" % k), "rb").read() for k in (1, 2))
     if case["src"] == "aligned":
-        return (aligned_reads(**case["aligned"])[1],)
+        return aligned_case(case)[1]
     blk = sf.make_block(**case["src"])
     t = sf.to_fastq(blk)
     t = t if case["pe"] else (t,)
@@ -137,6 +139,51 @@ def aligned_reads(n, seed, reads, L, Lmin=None, n_rate=0.0):
     return fa, b"".join(recs)
 
 
+def aligned_pairs(n, seed, pairs, L):
+    """(FASTA, FASTQ 1, FASTQ 2): pairs sampled from one random chromosome, inserts of 200..399 bp, 0..2 substitutions per mate,
+    mate 2 reverse-complemented, half of the pairs with the mates swapped, 8 % of the pairs random (unmapped)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ref = acgt[rng.integers(0, 4, n)]
+    fa = b">chr1\n" + b"".join(ref[i:i + 60].tobytes() + b"\n" for i in range(0, n, 60))
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+
+    def revcomp(s):
+        return np.array([comp[int(c)] for c in s[::-1]], np.uint8)
+
+    def mutate(s):
+        s = s.copy()
+        for _ in range(int(rng.integers(0, 3))):
+            s[int(rng.integers(0, L))] = acgt[rng.integers(0, 4)]
+        return s
+
+    r1, r2 = [], []
+    for i in range(pairs):
+        q1 = np.clip(np.rint(rng.normal(30, 6, L)), 2, 40).astype(np.uint8) + 33
+        q2 = np.clip(np.rint(rng.normal(30, 6, L)), 2, 40).astype(np.uint8) + 33
+        if rng.random() < 0.08:
+            a, b = acgt[rng.integers(0, 4, L)], acgt[rng.integers(0, 4, L)]
+        else:
+            ins = int(rng.integers(200, 400))
+            p = int(rng.integers(0, n - ins))
+            a, b = mutate(ref[p:p + L]), revcomp(mutate(ref[p + ins - L:p + ins]))
+            if rng.random() < 0.5:
+                a, b = b, a
+        r1.append(b"@p%d/1\n" % i + a.tobytes() + b"\n+\n" + q1.tobytes() + b"\n")
+        r2.append(b"@p%d/2\n" % i + b.tobytes() + b"\n+\n" + q2.tobytes() + b"\n")
+    return fa, b"".join(r1), b"".join(r2)
+
+
+def aligned_case(case):
+    """(FASTA, (FASTQ, ...)) of a case whose reads are sampled from its own reference."""
+    if case["pe"]:
+        fa, f1, f2 = aligned_pairs(**case["aligned"])
+        return fa, (f1, f2)
+    fa, fq = aligned_reads(**case["aligned"])
+    return fa, (fq,)
+
+
 def random_reference(n, seed):
     """FASTA text of one random chromosome (numpy default_rng(seed), 60 bases per line)."""
     import numpy as np
@@ -173,7 +220,7 @@ def main():
             args = ["-c", "-t", "1", "-f"] + case["opts"]
             ref_md5 = None
             if case.get("ref"):     # `SeqArc -i` writes a ~2 GB hash index beside the FASTA (temporary)
-                fa = aligned_reads(**case["aligned"])[0] if case.get("aligned") else random_reference(**case["ref"])
+                fa = aligned_case(case)[0] if case.get("aligned") else random_reference(**case["ref"])
                 open(os.path.join(tmp, "ref.fa"), "wb").write(fa)
                 rc, log = po.run_ref(["-i", "ref.fa"], tmp)
                 assert rc == 0, log[-2000:]
