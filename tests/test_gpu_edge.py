@@ -206,7 +206,7 @@ def test_block_with_mapped_reads_is_refused_not_misdecoded(fq):
     mapped reads must come back SQ_ERR_FORMAT, next to an ordinary block that decodes."""
     import os
     from oracle import arcwalk
-    name = common.ALIGNED[0]
+    name = "aligned_se100"
     arc = arcwalk.parse_arc(open(os.path.join(common.GOLD, name + ".arc"), "rb").read())
     aligned = arc["blocks"][0]["raw"]
     codec = fq.EncapFqzComp(workspace_bytes=1 << 30)
