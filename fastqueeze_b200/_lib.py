@@ -18,7 +18,8 @@ STATUS = {0: "SQ_OK", -1: "SQ_ERR_NO_DEVICE", -2: "SQ_ERR_CUDA", -3: "SQ_ERR_ARG
 # every symbol include/seqarc_b200.h declares
 EXPORTS = ["sq_create", "sq_destroy", "sq_last_error", "sq_load_model", "sq_model_size", "sq_train_model", "sq_encode_blocks",
            "sq_encode_blocks_dev", "sq_decode_blocks", "sq_decode_blocks_dev", "sq_rblock", "sq_last_timings",
-           "sq_last_launches", "sq_last_wave_blocks", "sq_debug_fetch", "sq_device_count", "sq_version"]
+           "sq_last_launches", "sq_last_wave_blocks", "sq_debug_fetch", "sq_device_count", "sq_version",
+           "sq_side_encode", "sq_side_decode"]
 
 
 class SqParams(C.Structure):
@@ -42,6 +43,11 @@ class SqBlockDec(C.Structure):
                 ("seqcap", C.c_uint64), ("idlen", C.c_void_p), ("seqlen", C.c_void_p), ("readcap", C.c_uint32),
                 ("nreads", C.c_uint32), ("idbytes", C.c_uint64), ("seqbytes", C.c_uint64), ("status", C.c_int32),
                 ("longflag", C.c_int32)]
+
+
+class SqSideStream(C.Structure):
+    _fields_ = [("model", C.c_int32), ("nsym", C.c_uint32), ("sym", C.c_void_p), ("bytes", C.c_void_p),
+                ("cap", C.c_uint64), ("len", C.c_uint64), ("status", C.c_int32)]
 
 
 class SeqArcB200Error(RuntimeError):
@@ -92,6 +98,10 @@ def lib():
     L.sq_last_wave_blocks.argtypes = [C.c_void_p]
     L.sq_debug_fetch.restype = C.c_int
     L.sq_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    for n in ("sq_side_encode", "sq_side_decode"):
+        f = getattr(L, n)
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(SqSideStream), C.c_int]
     L.sq_device_count.restype = C.c_int
     L.sq_device_count.argtypes = []
     L.sq_version.restype = C.c_char_p

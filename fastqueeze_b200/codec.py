@@ -218,6 +218,40 @@ class EncapFqzComp:
             raise self._err(rc)
         return q
 
+    # Aligned-mode side streams (compressOrder @0x424b70, compressPERelation @0x422be0, compressAlignInfo_* @0x425d70-0x426c0f
+    # and their decompress* twins): all streams of one call are coded in one launch.
+    def compressSideStreams(self, streams):
+        """streams: [(N, uint8 array)] -> [bytes], the bare range-coder output of each array through a fresh SIMPLE_MODEL<N>."""
+        n = len(streams)
+        ss = (_lib.SqSideStream * n)()
+        keep = []
+        for i, (model, sym) in enumerate(streams):
+            a = np.ascontiguousarray(sym, dtype=np.uint8)
+            out = np.empty(a.shape[0] + 16, np.uint8)
+            keep.append((a, out))
+            ss[i].model, ss[i].nsym, ss[i].sym = model, a.shape[0], a.ctypes.data if a.shape[0] else None
+            ss[i].bytes, ss[i].cap = out.ctypes.data, out.shape[0]
+        rc = self._L.sq_side_encode(self._h, ss, n)
+        if rc != 0:
+            raise self._err(rc)
+        return [keep[i][1][:ss[i].len].tobytes() for i in range(n)]
+
+    def decompressSideStreams(self, streams):
+        """streams: [(N, bytes, nsym)] -> [uint8 array of nsym symbols]."""
+        n = len(streams)
+        ss = (_lib.SqSideStream * n)()
+        keep = []
+        for i, (model, data, nsym) in enumerate(streams):
+            b = np.frombuffer(data, np.uint8).copy()
+            out = np.empty(nsym, np.uint8)
+            keep.append((b, out))
+            ss[i].model, ss[i].nsym, ss[i].sym = model, nsym, out.ctypes.data if nsym else None
+            ss[i].bytes, ss[i].cap = b.ctypes.data, b.shape[0]
+        rc = self._L.sq_side_decode(self._h, ss, n)
+        if rc != 0:
+            raise self._err(rc)
+        return [k[1] for k in keep]
+
     # test hook
     def debug_triples(self, which, block=0):
         cnt = np.zeros(3, np.uint64)

@@ -894,6 +894,112 @@ int decode_blocks(sq_ctx *c, const u8 *const *recs, const u64 *reclens, int n, s
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Aligned-mode side streams: compressOrder @0x424b70, compressPERelation @0x422be0, compressAlignInfo_{Pos, Mis, Rev,
+// CigaL, CigaV} @0x425d70-0x426c0f and their decompress* twins.  Each stream is one serial chain (a fresh SIMPLE_MODEL<N>,
+// N <= 16, the model in registers / local memory): one thread per stream, all streams of the call in one launch.
+namespace {
+
+struct SideJob { const u8 *sym_in; u8 *sym_out; const u8 *bytes_in; u8 *bytes_out; u64 cap; u32 nsym; i32 model; u64 len; i32 status; };
+
+template <int N>
+__device__ void side_encode_n(SideJob &j) {
+    SmModel<N> m;
+    m.init();
+    RcEnc rc;
+    rc.start(j.bytes_out, j.bytes_out + j.cap);
+    for (u32 i = 0; i < j.nsym; i++) {
+        u32 s = j.sym_in[i];
+        if (s >= (u32)N) { j.status = SQ_ERR_INPUT; return; }
+        m.encode(rc, s);
+    }
+    rc.finish();
+    j.len = (u64)(rc.out - j.bytes_out);
+    j.status = rc.overflow ? SQ_ERR_CAPACITY : SQ_OK;
+}
+template <int N>
+__device__ void side_decode_n(SideJob &j) {
+    SmModel<N> m;
+    m.init();
+    RcDec rc;
+    rc.start(j.bytes_in, j.bytes_in + j.cap);
+    for (u32 i = 0; i < j.nsym; i++) j.sym_out[i] = (u8)m.decode(rc);
+    j.len = j.cap;
+    j.status = SQ_OK;
+}
+template <bool ENC, int N>
+__device__ void side_run(SideJob &j) { if (ENC) side_encode_n<N>(j); else side_decode_n<N>(j); }
+
+template <bool ENC>
+__global__ void k_side_streams(SideJob *jobs, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SideJob j = jobs[i];
+    switch (j.model) {          // the sizes the reference uses get their own instance; the rest share the largest
+        case 2: side_run<ENC, 2>(j); break;
+        case 4: side_run<ENC, 4>(j); break;
+        case 5: side_run<ENC, 5>(j); break;
+        case 8: side_run<ENC, 8>(j); break;
+        case 9: side_run<ENC, 9>(j); break;
+        default: j.status = SQ_ERR_ARG; break;
+    }
+    jobs[i].len = j.len;
+    jobs[i].status = j.status;
+}
+
+int side_streams(sq_ctx *c, sq_side_stream *ss, int n, bool enc) {
+    if (!c || !ss || n <= 0) { if (c) c->err = "bad argument"; return SQ_ERR_ARG; }
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    for (int i = 0; i < n; i++) {
+        const int N = ss[i].model;
+        if (!(N == 2 || N == 4 || N == 5 || N == 8 || N == 9) || (ss[i].nsym && !ss[i].sym) || !ss[i].bytes || (!enc && ss[i].cap < 8)) {
+            c->err = "side stream: model size must be 2, 4, 5, 8 or 9, buffers non-null, a stream at least 8 bytes"; return SQ_ERR_ARG;
+        }
+    }
+    Arena &A = c->arena;
+    A.reset();
+    c->last_valid = false;
+    cudaStream_t st = c->stream;
+    std::vector<SideJob> jobs(n);
+    SideJob *d_jobs = (SideJob *)A.take(sizeof(SideJob) * (u64)n);
+    bool ok = d_jobs != nullptr;
+    for (int i = 0; i < n && ok; i++) {
+        SideJob &j = jobs[i];
+        memset(&j, 0, sizeof j);
+        j.model = ss[i].model; j.nsym = ss[i].nsym; j.cap = ss[i].cap;
+        u8 *d_sym = (u8 *)A.take((u64)ss[i].nsym + 16), *d_bytes = (u8 *)A.take(ss[i].cap + 16);
+        if (!d_sym || !d_bytes) { ok = false; break; }
+        j.sym_in = j.sym_out = d_sym; j.bytes_in = j.bytes_out = d_bytes;
+        if (enc) { if (ss[i].nsym) CUDA_OK(c, cudaMemcpyAsync(d_sym, ss[i].sym, ss[i].nsym, cudaMemcpyHostToDevice, st)); }
+        else CUDA_OK(c, cudaMemcpyAsync(d_bytes, ss[i].bytes, ss[i].cap, cudaMemcpyHostToDevice, st));
+    }
+    if (!ok) { c->err = "side streams do not fit the device workspace"; return SQ_ERR_NOMEM; }
+    CUDA_OK(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(SideJob) * (u64)n, cudaMemcpyHostToDevice, st));
+    if (enc) k_side_streams<true><<<(n + 31) / 32, 32, 0, st>>>(d_jobs, n);
+    else k_side_streams<false><<<(n + 31) / 32, 32, 0, st>>>(d_jobs, n);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches = 1;
+    std::vector<SideJob> res(n);
+    CUDA_OK(c, cudaMemcpyAsync(res.data(), d_jobs, sizeof(SideJob) * (u64)n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    int worst = SQ_OK;
+    for (int i = 0; i < n; i++) {
+        ss[i].status = res[i].status;
+        ss[i].len = res[i].status == SQ_OK ? res[i].len : 0;
+        if (res[i].status != SQ_OK) { if (!worst) worst = res[i].status; continue; }
+        if (enc) CUDA_OK(c, cudaMemcpyAsync(ss[i].bytes, jobs[i].bytes_out, res[i].len, cudaMemcpyDeviceToHost, st));
+        else if (ss[i].nsym) CUDA_OK(c, cudaMemcpyAsync(ss[i].sym, jobs[i].sym_out, ss[i].nsym, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    if (worst) c->err = "one or more side streams failed; see per-stream status";
+    return worst;
+}
+
+}  // namespace
+
+extern "C" int sq_side_encode(sq_ctx *c, sq_side_stream *streams, int n) { return side_streams(c, streams, n, true); }
+extern "C" int sq_side_decode(sq_ctx *c, sq_side_stream *streams, int n) { return side_streams(c, streams, n, false); }
+
 extern "C" int sq_decode_blocks(sq_ctx *c, const uint8_t *const *recs, const uint64_t *reclens, int n, sq_block_dec *out) {
     return decode_blocks(c, recs, reclens, n, out, true);
 }

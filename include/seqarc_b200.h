@@ -129,6 +129,27 @@ int  sq_decode_blocks_dev(sq_ctx *c, const uint8_t *const *recs, const uint64_t 
  * quality bytes, in place, HOST buffer). */
 int  sq_rblock(sq_ctx *c, uint8_t *qual, uint64_t n, double r);
 
+/* Aligned-mode side streams (doAlignEncode @0x42d4c0 / doAlignDecode @0x42c8d0): a block that holds mapped reads carries
+ * the aligner's arrays as small streams, each the bare range-coder output of a byte array through a fresh SIMPLE_MODEL<N>
+ * (no count in front; the counts travel in their own tags).  These two calls stand where
+ *   compressOrder @0x424b70 (tag 8, N = 5), compressPERelation @0x422be0 (tag 9, N = 4),
+ *   compressAlignInfo_Pos @0x425d70 (11, N = 2), _Mis @0x425ff0 (15, N = 8 or 9), _Rev @0x426480 (10, N = 2),
+ *   _CigaL @0x426700 (12, N = 2), _CigaV @0x426980 (13, N = 4)
+ * and their decompress* twins (@0x42b130 ... @0x42c3b0) stand in the reference.  All streams of a call are coded at once,
+ * one chain each.  Buffers are HOST memory.  Alignment itself and the block framing of aligned blocks are not part of
+ * this library yet: sq_decode_blocks answers SQ_ERR_FORMAT for a block with mapped reads. */
+typedef struct sq_side_stream {
+    int32_t  model;          /* N of SIMPLE_MODEL<N>: 2, 4, 5, 8 or 9 */
+    uint32_t nsym;           /* symbols in the array */
+    uint8_t *sym;            /* encode: in (every value < model); decode: out, nsym bytes */
+    uint8_t *bytes;          /* encode: out, `cap` bytes available (nsym + 16 always suffices); decode: in */
+    uint64_t cap;            /* encode: capacity of `bytes`; decode: length of the stream */
+    uint64_t len;            /* encode: out, bytes written */
+    int32_t  status;         /* out: SQ_OK, SQ_ERR_CAPACITY, SQ_ERR_INPUT (a symbol >= model) */
+} sq_side_stream;
+int  sq_side_encode(sq_ctx *c, sq_side_stream *streams, int n);
+int  sq_side_decode(sq_ctx *c, sq_side_stream *streams, int n);
+
 /* Measurement hooks (DebugInfo @0x420080 stands here in the reference): device time of the
  * kernels of the last encode / decode call, per stage, in milliseconds (CUDA events on the
  * context's stream).  names[i] are static strings; returns the number of stages filled. */
