@@ -19,7 +19,7 @@ STATUS = {0: "SQ_OK", -1: "SQ_ERR_NO_DEVICE", -2: "SQ_ERR_CUDA", -3: "SQ_ERR_ARG
 EXPORTS = ["sq_create", "sq_destroy", "sq_last_error", "sq_load_model", "sq_model_size", "sq_train_model", "sq_encode_blocks",
            "sq_encode_blocks_dev", "sq_decode_blocks", "sq_decode_blocks_dev", "sq_rblock", "sq_last_timings",
            "sq_last_launches", "sq_last_wave_blocks", "sq_debug_fetch", "sq_device_count", "sq_version",
-           "sq_side_encode", "sq_side_decode"]
+           "sq_side_encode", "sq_side_decode", "sq_set_reference", "sq_align_rebuild"]
 
 
 class SqParams(C.Structure):
@@ -48,6 +48,14 @@ class SqBlockDec(C.Structure):
 class SqSideStream(C.Structure):
     _fields_ = [("model", C.c_int32), ("nsym", C.c_uint32), ("sym", C.c_void_p), ("bytes", C.c_void_p),
                 ("cap", C.c_uint64), ("len", C.c_uint64), ("status", C.c_int32)]
+
+
+class SqAlignBlock(C.Structure):
+    _fields_ = [("nreads", C.c_uint32), ("pe", C.c_int32), ("seqlen", C.c_void_p), ("order", C.c_void_p), ("pos", C.c_void_p),
+                ("mis", C.c_void_p), ("rev", C.c_void_p), ("cigal", C.c_void_p), ("cigav", C.c_void_p), ("perel", C.c_void_p),
+                ("npos", C.c_uint32), ("nalign", C.c_uint32), ("ncigal", C.c_uint32), ("ncigav", C.c_uint32),
+                ("nperel", C.c_uint32), ("insbits", C.c_uint32), ("seq", C.c_void_p), ("seqbytes", C.c_uint64),
+                ("status", C.c_int32)]
 
 
 class SeqArcB200Error(RuntimeError):
@@ -102,6 +110,10 @@ def lib():
         f = getattr(L, n)
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.POINTER(SqSideStream), C.c_int]
+    L.sq_set_reference.restype = C.c_int
+    L.sq_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.sq_align_rebuild.restype = C.c_int
+    L.sq_align_rebuild.argtypes = [C.c_void_p, C.POINTER(SqAlignBlock), C.c_int]
     L.sq_device_count.restype = C.c_int
     L.sq_device_count.argtypes = []
     L.sq_version.restype = C.c_char_p

@@ -252,6 +252,37 @@ class EncapFqzComp:
             raise self._err(rc)
         return [k[1] for k in keep]
 
+    # Aligned mode, decode side: mapped reads rebuilt from the reference (getRealPos @0x42de30, AlignInfoToSeq @0x42e020)
+    def set_reference(self, fasta: bytes):
+        """The reference FASTA the archive was written against: header lines dropped, sequences concatenated, uploaded once."""
+        seq = np.frombuffer(b"".join(l for l in fasta.split(b"\n") if l and not l.startswith(b">")), np.uint8).copy()
+        rc = self._L.sq_set_reference(self._h, seq.ctypes.data, seq.shape[0])
+        if rc != 0:
+            raise self._err(rc)
+
+    def alignRebuild(self, blocks):
+        """blocks: [dict(seqlen, seq, pe, order, pos, mis, rev, cigal, cigav[, perel, insbits])] -> [seq array] with the mapped
+        reads' bases filled in (Pos / CigaL are bit arrays, one bit per byte; the other reads' bytes are left as given)."""
+        n = len(blocks)
+        bl = (_lib.SqAlignBlock * n)()
+        keep = []
+        for i, b in enumerate(blocks):
+            a = {k: np.ascontiguousarray(b.get(k, np.zeros(0, np.uint8)), np.uint8) for k in ("order", "pos", "mis", "rev", "cigal", "cigav", "perel")}
+            a["seqlen"] = np.ascontiguousarray(b["seqlen"], np.int32)
+            a["seq"] = np.ascontiguousarray(b["seq"], np.uint8).copy()
+            keep.append(a)
+            ptr = lambda k: a[k].ctypes.data if a[k].shape[0] else None      # noqa: E731
+            bl[i].nreads, bl[i].pe = a["seqlen"].shape[0], int(bool(b.get("pe", 0)))
+            bl[i].seqlen, bl[i].order, bl[i].pos, bl[i].mis, bl[i].rev = ptr("seqlen"), ptr("order"), ptr("pos"), ptr("mis"), ptr("rev")
+            bl[i].cigal, bl[i].cigav, bl[i].perel = ptr("cigal"), ptr("cigav"), ptr("perel")
+            bl[i].npos, bl[i].nalign, bl[i].ncigal = a["pos"].shape[0], a["mis"].shape[0], a["cigal"].shape[0]
+            bl[i].ncigav, bl[i].nperel, bl[i].insbits = a["cigav"].shape[0], a["perel"].shape[0], int(b.get("insbits", 0))
+            bl[i].seq, bl[i].seqbytes = ptr("seq"), a["seq"].shape[0]
+        rc = self._L.sq_align_rebuild(self._h, bl, n)
+        if rc != 0:
+            raise self._err(rc)
+        return [k["seq"] for k in keep]
+
     # test hook
     def debug_triples(self, which, block=0):
         cnt = np.zeros(3, np.uint64)

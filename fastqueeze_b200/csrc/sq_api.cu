@@ -66,6 +66,8 @@ struct sq_ctx {
     std::string err;
     // model snapshot
     u8 *d_model = nullptr;
+    u8 *d_ref = nullptr;              // aligned mode: the concatenated reference sequence (sq_set_reference)
+    u64 ref_len = 0;
     u64 model_len = 0;
     // measurement
     StageTimer timer;
@@ -161,6 +163,7 @@ extern "C" void sq_destroy(sq_ctx *c) {
     c->timer.destroy();
     if (c->arena.base) cudaFree(c->arena.base);
     if (c->d_model) cudaFree(c->d_model);
+    if (c->d_ref) cudaFree(c->d_ref);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -996,6 +999,173 @@ int side_streams(sq_ctx *c, sq_side_stream *ss, int n, bool enc) {
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Aligned mode, decode side: the bases of mapped reads from the reference (getRealPos @0x42de30, AlignInfoToSeq @0x42e020).
+// k_align_walk: one thread per block walks its reads in order -- positions and mismatch offsets are variable-width bit
+// fields, so where read j's fields start depends on every read before it -- and leaves one descriptor per mapped read.
+// k_align_fill: one warp per mapped read copies the reference segment (coalesced), applies its substitutions, reverses and
+// complements: the part that touches every base runs at memory speed.
+namespace {
+
+struct AlignDesc { u64 pos, off; i32 len; u32 cl_off, cv_off; u8 rev, nmis; };
+struct AlignJob {
+    u32 nreads; i32 pe;
+    const i32 *seqlen; const u8 *order, *pos, *mis, *rev, *cigal, *cigav, *perel;
+    u32 npos, nalign, ncigal, ncigav, nperel, insbits;
+    u8 *seq; u64 seqbytes;
+    AlignDesc *desc; i32 status; u32 nmapped;
+};
+
+SQ_HD u32 bitnum64(u64 v) { u32 n = 0; while (v) { n++; v >>= 1; } return n; }        // getbitnum @0x40d470
+SQ_D u64 read_bits(const u8 *bits, u32 nbits, u32 &cur, u32 w) {                    // LSB first (getOffsePos @0x42ec80, getCigal @0x42ecc0)
+    u64 v = 0;
+    for (u32 k = 0; k < w; k++) if (cur + k < nbits) v += (u64)bits[cur + k] << k;
+    cur += w;
+    return v;
+}
+
+__global__ void k_align_walk(AlignJob *jobs, int n, u64 reflen) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    AlignJob &J = jobs[b];
+    const u32 W = bitnum64(reflen) > 2 ? bitnum64(reflen) - 2 : 0;                   // SeqArcParam+0x1858
+    u32 pc = 0, cl = 0, cv = 0, j = 0, pr = 0;
+    u64 cur = 0, off = 0;
+    i32 status = SQ_OK;
+    for (u32 i = 0; i < J.nreads && status == SQ_OK; i++) {
+        const i32 len = J.seqlen[i];
+        if (len < 0 || off + (u64)len > J.seqbytes) { status = SQ_ERR_FORMAT; break; }
+        const u32 o = J.order[i];
+        if (o) {
+            if (j >= J.nalign || o > 4) { status = SQ_ERR_FORMAT; break; }
+            const bool second = J.pe && (i & 1) && J.order[i - 1];
+            u64 pos;
+            if (!second) pos = read_bits(J.pos, J.npos, pc, W) + ((u64)(o - 1) << W);
+            else {
+                const u32 rel = pr < J.nperel ? J.perel[pr] : 4u;
+                pr++;
+                pos = cur;
+                if (rel == 1) pos += read_bits(J.pos, J.npos, pc, J.insbits);
+                else if (rel == 0) pos -= read_bits(J.pos, J.npos, pc, J.insbits);
+                else if (rel == 2) pos = read_bits(J.pos, J.npos, pc, bitnum64(cur));
+                else if (rel == 3) pos += read_bits(J.pos, J.npos, pc, bitnum64(reflen - cur));
+            }
+            cur = pos;
+            const u32 nmis = J.mis[j];
+            if (pos < 1 || pos - 1 + (u64)len > reflen || nmis > 16 || pc > J.npos) { status = SQ_ERR_FORMAT; break; }
+            AlignDesc d;
+            d.pos = pos; d.off = off; d.len = len; d.cl_off = cl; d.cv_off = cv; d.rev = J.rev[j]; d.nmis = (u8)nmis;
+            u32 prev = 0;
+            for (u32 m = 0; m < nmis; m++) prev += (u32)read_bits(J.cigal, J.ncigal, cl, bitnum64((u64)(len - (i32)prev)));
+            cv += nmis;
+            if (cl > J.ncigal || cv > J.ncigav) { status = SQ_ERR_FORMAT; break; }
+            J.desc[j++] = d;
+        }
+        off += (u64)len;
+    }
+    J.status = status;
+    J.nmapped = status == SQ_OK ? j : 0;
+}
+
+__global__ void __launch_bounds__(128) k_align_fill(const AlignJob *jobs, const u8 *ref) {
+    const AlignJob &J = jobs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 j = warp; j < J.nmapped; j += nwarps) {
+        const AlignDesc d = J.desc[j];
+        u32 where[16], var[16];
+        u32 cl = d.cl_off, prev = 0;
+        for (u32 m = 0; m < d.nmis; m++) {                // a handful of bit fields: every lane decodes them
+            prev += (u32)read_bits(J.cigal, J.ncigal, cl, bitnum64((u64)(d.len - (i32)prev)));
+            where[m] = prev;
+            var[m] = J.cigav[d.cv_off + m];
+        }
+        for (i32 k = lane; k < d.len; k += 32) {
+            u32 code = seq_val(ref[d.pos - 1 + (u64)k]);
+            if (code > 3) code = 4;
+            for (u32 m = 0; m < d.nmis; m++)
+                if (where[m] == (u32)k) {                 // mapvar2base @0x40db20: which of the three other bases, 3 = N
+                    const u32 v = var[m];
+                    const u32 tab = code == 0 ? 0x4312u : code == 1 ? 0x4302u : code == 2 ? 0x4301u : code == 3 ? 0x4012u : 0x0000u;
+                    code = (tab >> (4 * (v & 3))) & 15u;
+                }
+            const u32 out = d.rev ? (u32)(d.len - 1 - k) : (u32)k;
+            const u32 c2 = code > 3 ? 4u : (d.rev ? 3u - code : code);     // getch @0x40dc50
+            J.seq[d.off + out] = (u8)"ACGTN"[c2];
+        }
+    }
+}
+
+int align_rebuild(sq_ctx *c, sq_align_block *bl, int n) {
+    if (!c || !bl || n <= 0) { if (c) c->err = "bad argument"; return SQ_ERR_ARG; }
+    if (!c->d_ref) { c->err = "no reference loaded (sq_set_reference)"; return SQ_ERR_ARG; }
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    Arena &A = c->arena;
+    A.reset();
+    c->last_valid = false;
+    cudaStream_t st = c->stream;
+    std::vector<AlignJob> jobs(n);
+    AlignJob *d_jobs = (AlignJob *)A.take(sizeof(AlignJob) * (u64)n);
+    bool ok = d_jobs != nullptr;
+    u32 maxalign = 0;
+    auto up = [&](const void *h, u64 bytes) -> u8 * {
+        u8 *d = (u8 *)A.take(bytes + 16);
+        if (!d) { ok = false; return nullptr; }
+        if (bytes && cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+        return d;
+    };
+    for (int i = 0; i < n && ok; i++) {
+        const sq_align_block &b = bl[i];
+        if (!b.seqlen || !b.order || !b.seq || (b.npos && !b.pos) || (b.nalign && (!b.mis || !b.rev)) || (b.ncigal && !b.cigal) ||
+            (b.ncigav && !b.cigav) || (b.nperel && !b.perel)) { c->err = "sq_align_block: null array"; return SQ_ERR_ARG; }
+        AlignJob &j = jobs[i];
+        memset(&j, 0, sizeof j);
+        j.nreads = b.nreads; j.pe = b.pe;
+        j.npos = b.npos; j.nalign = b.nalign; j.ncigal = b.ncigal; j.ncigav = b.ncigav; j.nperel = b.nperel; j.insbits = b.insbits;
+        j.seqbytes = b.seqbytes;
+        j.seqlen = (const i32 *)up(b.seqlen, 4ull * b.nreads);
+        j.order = up(b.order, b.nreads); j.pos = up(b.pos, b.npos); j.mis = up(b.mis, b.nalign); j.rev = up(b.rev, b.nalign);
+        j.cigal = up(b.cigal, b.ncigal); j.cigav = up(b.cigav, b.ncigav); j.perel = up(b.perel, b.nperel);
+        j.seq = up(b.seq, b.seqbytes);
+        j.desc = (AlignDesc *)A.take(sizeof(AlignDesc) * ((u64)b.nalign + 1));
+        if (!j.desc) ok = false;
+        maxalign = std::max(maxalign, b.nalign);
+    }
+    if (!ok) { c->err = "aligned blocks do not fit the device workspace"; return SQ_ERR_NOMEM; }
+    CUDA_OK(c, cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(AlignJob) * (u64)n, cudaMemcpyHostToDevice, st));
+    k_align_walk<<<(n + 31) / 32, 32, 0, st>>>(d_jobs, n, c->ref_len);
+    CUDA_OK(c, cudaGetLastError());
+    const u32 gx = std::max<u32>(1, std::min<u32>((maxalign + 3) / 4, (u32)(c->nsm > 0 ? c->nsm : 148) * 8));
+    k_align_fill<<<dim3(gx, n), 128, 0, st>>>(d_jobs, c->d_ref);
+    CUDA_OK(c, cudaGetLastError());
+    c->launches = 2;
+    std::vector<AlignJob> res(n);
+    CUDA_OK(c, cudaMemcpyAsync(res.data(), d_jobs, sizeof(AlignJob) * (u64)n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    int worst = SQ_OK;
+    for (int i = 0; i < n; i++) {
+        bl[i].status = res[i].status;
+        if (res[i].status != SQ_OK) { if (!worst) worst = res[i].status; continue; }
+        if (bl[i].seqbytes) CUDA_OK(c, cudaMemcpyAsync(bl[i].seq, jobs[i].seq, bl[i].seqbytes, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(c, cudaStreamSynchronize(st));
+    if (worst) c->err = "one or more aligned blocks are inconsistent; see per-block status";
+    return worst;
+}
+
+}  // namespace
+
+extern "C" int sq_set_reference(sq_ctx *c, const uint8_t *bases, uint64_t n) {
+    if (!c || !bases || !n) { if (c) c->err = "bad argument"; return SQ_ERR_ARG; }
+    CUDA_OK(c, cudaSetDevice(c->p.device));
+    if (c->d_ref) { cudaFree(c->d_ref); c->d_ref = nullptr; c->ref_len = 0; }
+    CUDA_OK(c, cudaMalloc((void **)&c->d_ref, n + 16));
+    CUDA_OK(c, cudaMemcpy(c->d_ref, bases, n, cudaMemcpyHostToDevice));
+    c->ref_len = n;
+    return SQ_OK;
+}
+extern "C" int sq_align_rebuild(sq_ctx *c, sq_align_block *blocks, int n) { return align_rebuild(c, blocks, n); }
 
 extern "C" int sq_side_encode(sq_ctx *c, sq_side_stream *streams, int n) { return side_streams(c, streams, n, true); }
 extern "C" int sq_side_decode(sq_ctx *c, sq_side_stream *streams, int n) { return side_streams(c, streams, n, false); }

@@ -150,6 +150,30 @@ typedef struct sq_side_stream {
 int  sq_side_encode(sq_ctx *c, sq_side_stream *streams, int n);
 int  sq_side_decode(sq_ctx *c, sq_side_stream *streams, int n);
 
+/* Aligned mode, decode side: the bases of the MAPPED reads of a block, rebuilt from the reference (getRealPos @0x42de30 +
+ * AlignInfoToSeq @0x42e020 without its degenerate-base overlay).  sq_set_reference uploads the concatenated reference
+ * sequence (ASCII bases, header lines removed) once; it stays in HBM until sq_destroy.  sq_align_rebuild takes the decoded
+ * side arrays of each block (HOST memory; Pos and CigaL are bit arrays, one bit per byte) and fills `seq` at the offsets of
+ * the mapped reads; the bytes of unmapped reads are left as they were. */
+typedef struct sq_align_block {
+    uint32_t nreads;           /* reads of the block (paired-end: interleaved R1, R2, ...) */
+    int32_t  pe;               /* 1: paired-end (PERelation / insbits used for second mates) */
+    const int32_t *seqlen;     /* nreads */
+    const uint8_t *order;      /* nreads: 0 = not mapped, else 1 + the high bits of the position */
+    const uint8_t *pos;        /* npos bits */
+    const uint8_t *mis;        /* nalign: mismatches of each mapped read (at most 16) */
+    const uint8_t *rev;        /* nalign: strand */
+    const uint8_t *cigal;      /* ncigal bits: mismatch offsets */
+    const uint8_t *cigav;      /* ncigav: which other base each mismatch is */
+    const uint8_t *perel;      /* nperel: relation of a second mate to the first (pairs mapped with both mates) */
+    uint32_t npos, nalign, ncigal, ncigav, nperel, insbits;
+    uint8_t *seq;              /* in / out: the block's concatenated bases */
+    uint64_t seqbytes;
+    int32_t  status;           /* out: SQ_OK or SQ_ERR_FORMAT (arrays inconsistent, a position outside the reference) */
+} sq_align_block;
+int  sq_set_reference(sq_ctx *c, const uint8_t *bases, uint64_t n);
+int  sq_align_rebuild(sq_ctx *c, sq_align_block *blocks, int n);
+
 /* Measurement hooks (DebugInfo @0x420080 stands here in the reference): device time of the
  * kernels of the last encode / decode call, per stage, in milliseconds (CUDA events on the
  * context's stream).  names[i] are static strings; returns the number of stages filled. */

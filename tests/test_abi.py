@@ -51,7 +51,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
     import subprocess
     from fastqueeze_b200 import _lib
     structs = {"sq_params": _lib.SqParams, "sq_block_in": _lib.SqBlockIn, "sq_block_out": _lib.SqBlockOut,
-               "sq_block_dec": _lib.SqBlockDec, "sq_side_stream": _lib.SqSideStream}
+               "sq_block_dec": _lib.SqBlockDec, "sq_side_stream": _lib.SqSideStream,
+               "sq_align_block": _lib.SqAlignBlock}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "seqarc_b200.h"', 'int main(void) {']
     for cname, ct in structs.items():
         src.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))

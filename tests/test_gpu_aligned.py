@@ -46,3 +46,37 @@ def test_side_stream_edge_cases():
     with pytest.raises(fq.SeqArcB200Error):                                 # a symbol the model does not hold
         codec.compressSideStreams([(4, np.array([0, 1, 7], np.uint8))])
     codec.close()
+
+
+@pytest.mark.parametrize("name", common.ALIGNED)
+def test_mapped_reads_are_rebuilt_from_the_reference(name):
+    """sq_align_rebuild against the input FASTQ: the side arrays of a reference-written block (read out by the oracle) and the
+    reference sequence give back the bases of every mapped read; unmapped reads are left alone."""
+    import fastqueeze_b200 as fq
+    from tools import make_golden as mg
+    m = common.MANIFEST[name]
+    fasta, fastq = mg.aligned_case(dict(pe=m["pe"], aligned=m["aligned"]))
+    rec = arcwalk.parse_arc(open(os.path.join(common.GOLD, name + ".arc"), "rb").read())["blocks"][0]["raw"]
+    o = po.Oracle(md5=1)
+    o.set_reference(fasta)
+    want = o.decode_block(rec)
+    arrays = o.align_arrays()
+    off = np.concatenate([[0], np.cumsum(want.seqlen)])
+    given = want.seq.copy()
+    mapped = np.zeros(given.shape[0], bool)
+    for i in np.nonzero(arrays["order"])[0]:
+        mapped[off[i]:off[i + 1]] = True
+    given[mapped] = ord("?")                                  # what the call has to fill in
+    codec = fq.EncapFqzComp(workspace_bytes=1 << 30)
+    codec.set_reference(fasta)
+    blk = dict(arrays, seqlen=want.seqlen, seq=given, pe=m["pe"])
+    got = codec.alignRebuild([blk, blk])                      # two blocks in one call
+    for g in got:
+        assert np.array_equal(g[~mapped], want.seq[~mapped])
+        diff = np.nonzero(g != want.seq)[0]
+        # the degenerate-base overlay is not part of this call: a mapped read's N may come back as N (coded as a mismatch) only
+        assert all(want.seq[k] == ord("N") for k in diff) and not (g == ord("?")).any()
+    bad = dict(blk, pos=arrays["pos"][:100])                  # truncated position bits: reported, not a crash
+    with pytest.raises(fq.SeqArcB200Error):
+        codec.alignRebuild([bad])
+    codec.close()
