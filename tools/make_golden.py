@@ -77,6 +77,9 @@ CASES = [
          ref=dict(n=200000, seed=11)),
     dict(name="aligned_se_var", src="aligned", pe=False, opts=[], config=None,
          aligned=dict(n=1000000, seed=12, reads=2500, L=150, Lmin=60, n_rate=0.004), ref=dict(n=1000000, seed=12)),
+    # three sequences in the FASTA: positions run through their plain concatenation
+    dict(name="aligned_se_multi", src="aligned", pe=False, opts=[], config=None,
+         aligned=dict(n=0, seed=31, reads=2000, L=100, chroms=[120000, 90001, 50030]), ref=dict(n=0, seed=31)),
     dict(name="aligned_pe100", src="aligned", pe=True, opts=[], config=None, aligned=dict(n=300000, seed=21, pairs=2000, L=100),
          ref=dict(n=300000, seed=21)),
     dict(name="illumina_pe150_q3s2", src=dict(kind="illumina_pe150", n_templates=800, seed=22, n_rate=0.001), pe=True, opts=[],
@@ -104,15 +107,21 @@ def plus_lines(text):
     return b"\n".join(lines)
 
 
-def aligned_reads(n, seed, reads, L, Lmin=None, n_rate=0.0):
+def aligned_reads(n, seed, reads, L, Lmin=None, n_rate=0.0, chroms=None):
     """(FASTA, FASTQ): one random chromosome and single-end reads sampled from it -- 0..2 substitutions each, half of them
     reverse-complemented, a tenth of the reads random (they stay unmapped).  One generator draws the reference first.
-    Lmin: read lengths uniform in [Lmin, L]; n_rate: bases turned into N with quality '#' (degenerate-base overlay)."""
+    Lmin: read lengths uniform in [Lmin, L]; n_rate: bases turned into N with quality '#' (degenerate-base overlay);
+    chroms: lengths of several sequences instead of one of n bases (70 bases per line, header lines with a comment)."""
     import numpy as np
     rng = np.random.default_rng(seed)
     acgt = np.frombuffer(b"ACGT", np.uint8)
-    ref = acgt[rng.integers(0, 4, n)]
-    fa = b">chr1\n" + b"".join(ref[i:i + 60].tobytes() + b"\n" for i in range(0, n, 60))
+    if chroms:
+        parts = [acgt[rng.integers(0, 4, k)] for k in chroms]
+        fa = b"".join(b">chr%d some text\n" % (k + 1) + b"".join(c[i:i + 70].tobytes() + b"\n" for i in range(0, len(c), 70))
+                      for k, c in enumerate(parts))
+    else:
+        ref = acgt[rng.integers(0, 4, n)]
+        fa = b">chr1\n" + b"".join(ref[i:i + 60].tobytes() + b"\n" for i in range(0, n, 60))
     comp = {65: 84, 67: 71, 71: 67, 84: 65}
     recs = []
     Lmax = L
@@ -123,6 +132,9 @@ def aligned_reads(n, seed, reads, L, Lmin=None, n_rate=0.0):
         if kind < 0.1:
             s = acgt[rng.integers(0, 4, L)]
         else:
+            if chroms:
+                ref = parts[int(rng.integers(0, len(parts)))]
+                n = len(ref)
             p = int(rng.integers(0, n - L))
             s = ref[p:p + L].copy()
             for _ in range(int(rng.integers(0, 3))):
