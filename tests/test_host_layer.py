@@ -221,3 +221,26 @@ def test_cli_argument_forms():
     assert parse("-c ref.fasta -1 a.fq -o out")["ref"] == "ref.fasta"
     assert parse("-d x.arc -o back") == dict(mode="d", ref="", in1="", in2="", arc="x.arc", out="back", lossy="0", md5="1")
     assert parse("-d -t 8 ref.fa x.arc back") == dict(mode="d", ref="ref.fa", in1="", in2="", arc="x.arc", out="back", lossy="0", md5="1")
+
+
+@pytest.mark.parametrize("name", common.CASES[:6] + common.ALIGNED)
+def test_arc_reader_finds_every_block_record(hl, name):
+    """ArcReader (what `seqarc_b200 -d` maps the archive with) against the container walker of the test side: block count,
+    record offsets and lengths, the flags of the trailer -- also for archives whose blocks hold mapped reads."""
+    hl.sqh_read_arc.restype = C.c_int
+    hl.sqh_read_arc.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_int]
+    m = common.MANIFEST[name]
+    data = common.case_archive(name) if name not in common.ALIGNED else open(os.path.join(common.GOLD, name + ".arc"), "rb").read()
+    arc = arcwalk.parse_arc(data)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "a.arc")
+        open(p, "wb").write(data)
+        flags = C.c_int(0)
+        off = np.zeros(64, np.uint64)
+        ln = np.zeros(64, np.uint32)
+        n = hl.sqh_read_arc(p.encode(), C.byref(flags), off.ctypes.data, ln.ctypes.data, 64)
+    assert n == len(arc["blocks"])
+    for i, b in enumerate(arc["blocks"][:64]):
+        assert data[int(off[i]):int(off[i]) + int(ln[i])] == b["raw"]
+    assert bool(flags.value & 1) == bool(m["pe"])
+    assert bool(flags.value & 8) == ("-n" not in m["opts"])
