@@ -564,6 +564,8 @@ static int do_decompress(const Opt &o) {
                 int rc = sq_decode_blocks(c, recs->data(), lens->data(), n, dec->data());
                 if (rc != SQ_OK) {
                     const char *w = rc == SQ_ERR_MD5_NAME ? "Name md5 unequal" : rc == SQ_ERR_MD5_SEQ ? "Seq md5 unequal" : rc == SQ_ERR_MD5_QUAL ? "Qual md5 unequal" : sq_last_error(c);
+                    if (rc == SQ_ERR_FORMAT && ar.p.has_ref)
+                        w = "a block holds reads mapped to the reference the archive was written against; this decoder does not rebuild them yet";
                     fail(std::string("decode: ") + w);
                     break;
                 }
